@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mind_the_gaps B200 hot path.
+
+Metric (BASELINE.json): celerite log-likelihood evaluations / s at N = 1000 points, J = 4
+(DampedRandomWalk + Lorentzian, the alternative model of the Protassov LRT), batched over emcee
+walkers / parameter sets.
+
+A "step" = one batched log-likelihood pass (kernel K1) over this rank's parameter sets:
+``--ensembles`` independent 64-walker ensembles of config C2 sharing one irregularly sampled
+lightcurve.  Weak scaling: every rank evaluates its own ensembles, no data-path
+collective.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+prints ONE JSON line (rank 0).  ``value`` = device-resident throughput (CUDA events, max over ranks);
+``e2e`` = the same metric through the public API (``GP.log_likelihood_batch`` -> C ABI
+``mtg_loglike_host``) with pinned HOST buffers, H2D + D2H inside the timed region.
+``--impl reference`` times the reference's CPU algorithm (the oracle's C restatement of celerite,
+OpenMP over series: celerite itself is not importable, see oracle/__init__.py) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_POINTS = 1000
+WALKERS = 64
+J_CELERITE = 4
+FLOPS_PER_EVAL = N_POINTS * (4 * J_CELERITE ** 2 + 12 * J_CELERITE + 5)      # N(4J^2+12J+5)
+J_COMPUTE = 3
+FLOPS_PER_EVAL_COMPUTE = N_POINTS * (4 * J_COMPUTE ** 2 + 12 * J_COMPUTE + 5)
+
+
+def workload(n_sets, seed):
+    """Config C2: window(1000, seed 2), DRW + Lorentzian, parameter sets = truth + N(0, 0.1)."""
+    from helpers import C2_BOUNDS, c2_truth, fake_lightcurve
+    t, y, dy, _ = fake_lightcurve(N_POINTS, 2)
+    rng = np.random.default_rng(seed)
+    truth = c2_truth()
+    lo = np.array([b[0] for b in C2_BOUNDS]); hi = np.array([b[1] for b in C2_BOUNDS])
+    p = np.clip(truth[None, :] + rng.normal(0.0, 0.1, (n_sets, 5)), lo, hi)
+    return t, y, dy, p, C2_BOUNDS
+
+
+def make_gp(t, y, dy, bounds):
+    from mind_the_gaps_b200.celerite import GP
+    from mind_the_gaps_b200.celerite.modeling import ConstantModel
+    from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+    from helpers import c2_truth
+    p = c2_truth()
+    kernel = DampedRandomWalk(p[0], p[1], bounds=bounds[:2]) + Lorentzian(p[2], p[3], p[4], bounds=bounds[2:])
+    gp = GP(kernel, mean=ConstantModel(float(np.mean(y)), bounds=[(float(np.min(y)), float(np.max(y)))]), fit_mean=False)
+    gp.compute(t, dy + 1e-12)      # gpmodelling.py:54
+    return gp
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason sampler for the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(n_sets_hint, seconds=10.0, nthreads=0):
+    """Evaluations/s of the oracle's C restatement of celerite on the host cores."""
+    from oracle import cref
+    spec = [("drw",), ("lorentzian",)]
+    t, y, dy, p, _ = workload(4096, 99)
+    cref.loglike_params(spec, p[:256], t, y, dy, nthreads=nthreads)          # load + warm
+    t0 = time.perf_counter(); cref.loglike_params(spec, p, t, y, dy, nthreads=nthreads); dt = time.perf_counter() - t0
+    rate = len(p) / dt
+    n = int(min(max(rate * seconds, 4096), n_sets_hint))
+    t, y, dy, p, _ = workload(n, 98)
+    t0 = time.perf_counter(); cref.loglike_params(spec, p, t, y, dy, nthreads=nthreads); dt = time.perf_counter() - t0
+    return n / dt, n, dt, cref.max_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import cref
+    spec = [("drw",), ("lorentzian",)]
+    n = args.ref_sample
+    t, y, dy, p, _ = workload(n, 7)
+    for _ in range(args.warmup):
+        cref.loglike_params(spec, p[:max(256, n // 8)], t, y, dy)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.loglike_params(spec, p, t, y, dy)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cores = cref.max_threads()
+    line = {
+        "impl": "reference", "metric": "celerite loglike evals/s (N=1k, J=4)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: N=1000 irregular points, DRW+Lorentzian (J=4), %d parameter sets per step "
+                               "(bounded sample of the GPU arm's batch)" % n},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d parameter sets x %d steps, oracle/celerite_ref.c (C restatement of celerite's "
+                                   "two-pass CholeskySolver, OpenMP over series); celerite itself not importable" % (n, args.steps)},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ensembles", type=int, default=4736, help="64-walker ensembles per GPU (4736 = 148 SMs x 32)")
+    ap.add_argument("--ref-sample", type=int, default=65536, help="parameter sets per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mind_the_gaps_b200 import _native
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    _native.check(_native.lib().mtg_set_device(local_rank))
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = WALKERS * args.ensembles
+    t, y, dy, p, bounds = workload(B, 1000 + rank)
+    gp = make_gp(t, y, dy, bounds)
+    model = gp.device_model()
+    lib = _native.lib()
+
+    # ---- device-resident leg (value): inputs already in HBM ------------------------------------
+    d_t = torch.from_numpy(t).to(dev); d_y = torch.from_numpy(y).to(dev)
+    d_diag = torch.from_numpy((dy + 1e-12) ** 2).to(dev)
+    d_p = torch.from_numpy(p).to(dev)
+    d_ll = torch.empty(B, dtype=torch.float64, device=dev)
+    d_st = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)      # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        _native.check(lib.mtg_loglike_dev(ctypes.byref(model), N_POINTS, 1, B, B, d_t.data_ptr(), d_y.data_ptr(),
+                                          d_diag.data_ptr(), None, d_p.data_ptr(), d_ll.data_ptr(), d_st.data_ptr(),
+                                          _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
+
+    def l2_flush():
+        _native.check(lib.mtg_l2_flush(flush.data_ptr(), flush.numel() * 8, stream.cuda_stream))
+
+    for _ in range(args.warmup):
+        l2_flush(); step()
+    torch.cuda.synchronize()
+    # FP64 FMA peak of this device, measured live (roofline denominator; not in MEASURED_PEAKS.json)
+    pk = ctypes.c_double(); pk_ms = ctypes.c_double()
+    _native.check(lib.mtg_fp64_peak_probe(ctypes.byref(pk), ctypes.byref(pk_ms)))
+
+    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.3)
+    launches0 = lib.mtg_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        l2_flush()                      # between timed iterations, outside the event pair
+        e0.record(stream); step(); e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    kernel_launches = int(lib.mtg_launch_count() - launches0) - args.steps          # minus the flush launches
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop()
+    ok = bool(torch.isfinite(d_ll).all().item()) and int((d_st != 0).sum().item()) == 0
+
+    # ---- e2e leg: public API, pinned host buffers, H2D + D2H inside the timed region --------------
+    h_p = _native.pinned_empty((B, 5)); h_p[:] = p
+    h_ll = _native.pinned_empty((B,))
+    for _ in range(2):
+        gp.log_likelihood_batch(y, h_p, apply_prior=True, out=h_ll)
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gp.log_likelihood_batch(y, h_p, apply_prior=True, out=h_ll)
+    e2e_s = time.perf_counter() - t0
+    h2d = B * 5 * 8 + 3 * N_POINTS * 8
+    d2h = B * 8 + B * 4
+
+    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(tt[0].item()), float(tt[1].item())
+
+    if rank == 0:
+        value = B * world * args.steps / (total_ms * 1e-3)
+        ms_per_step = total_ms / args.steps
+        achieved_tf = B * FLOPS_PER_EVAL / (ms_per_step * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = B * (5 * 8 + 8 + 4) + 3 * N_POINTS * 8
+        line = {
+            "metric": "celerite loglike evals/s (N=1k, J=4)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 (configs[1]): N=1000 irregular points, DRW+Lorentzian (celerite J=4, ndim=5), "
+                                   "%d ensembles x 64 emcee walkers = %d parameter sets per GPU per step, one shared "
+                                   "lightcurve; log_prior + log_likelihood (GPModelling._log_probability)" % (args.ensembles, B),
+                       "batch_per_gpu": B, "walkers": WALKERS, "ensembles_per_gpu": args.ensembles, "n_points": N_POINTS,
+                       "j_celerite": J_CELERITE, "j_computed": J_COMPUTE, "parallelism": "series-sharded x%d" % world,
+                       "l2": "256 MB flush write between timed iterations", "results_ok": ok},
+            "clocks": clocks,
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "GP.log_likelihood_batch -> mtg_loglike_host (pinned host buffers)"},
+            "gpu_launches": kernel_launches,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk.value, "unit": "TFLOP/s",
+                         "frac": achieved_tf / pk.value if pk.value else None, "traffic": None,
+                         "kernel": "k1_loglike<1,1,false,true>",
+                         "flops_per_eval": FLOPS_PER_EVAL, "flops_per_eval_computed_J3": FLOPS_PER_EVAL_COMPUTE,
+                         "peak_source": "mtg_fp64_peak_probe: DFMA microbenchmark measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, n, dt, cores = cpu_port_rate(B, seconds=10.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                    "sample": "%d of the same parameter sets in %.1f s, oracle/celerite_ref.c "
+                                              "(C restatement of celerite, OpenMP)" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/*
+ * mtg_b200.h -- C ABI of libmtg_b200.so: the B200 (sm_100a) implementation of the
+ * mind_the_gaps hot path (celerite semiseparable GP log-likelihood + gradient, batched
+ * L-BFGS MLE, lightcurve simulator, LRT statistics).
+ *
+ * The reference (andresgur/mind_the_gaps) is pure Python and has no FFI layer; the seam this
+ * library replaces is the Python object protocol between GPModelling / Simulator and their
+ * native third-party dependencies.  Each entry point cites the reference
+ * interface it stands in for.  INTEGRATION.md shows the ctypes stubs a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative MTG_E* code for argument errors and a
+ *     positive cudaError_t value for CUDA failures (mtg_last_error() gives the text).
+ *   - *_dev functions take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) without synchronising; they are re-entrant per
+ *     stream and keep no global state.
+ *   - *_host functions take HOST pointers, do their own H2D / D2H copies on an internal
+ *     stream and return after the result is in the caller's buffer.
+ *   - all floating point is IEEE binary64.
+ *   - per-series `status`: 0 ok, 1 covariance not positive definite (celerite LinAlgError),
+ *     2 non-finite result, 3 outside the prior box (only when bounds are applied).
+ *
+ * Data layout in HBM
+ *   t      [N]        observation times, shared by every series of a call (ascending)
+ *   y,diag [N][S]     TIME-MAJOR: element (n, s) at n*S + s, S = number of data sets.
+ *                     Series b reads data set  b / group  (group = series per data set:
+ *                     walkers of one lightcurve, multi-starts of one simulated lightcurve, or
+ *                     B when one lightcurve is shared by the whole batch, S = 1).
+ *   params [B][ndim]  row-major free (un-frozen) parameters, celerite parameter-vector order.
+ */
+#ifndef MTG_B200_H
+#define MTG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTG_VERSION 100
+#define MTG_MAX_TERMS 8
+#define MTG_MAX_PARAMS 24
+#define MTG_MAX_J 16
+
+/* error codes (negative) */
+#define MTG_EINVAL   (-1)   /* bad argument                                  */
+#define MTG_EUNSUP   (-2)   /* kernel structure not supported (J too large)  */
+#define MTG_ENODEV   (-3)   /* no CUDA device                                */
+#define MTG_ENOMEM   (-4)
+
+/* Kernel terms: log-parameter -> celerite coefficient maps.
+ * Cites: mind_the_gaps/models/celerite_models.py:7-34 (Lorentzian), :36-52 (Cosinus),
+ * :55-68 (DampedRandomWalk), :71-90 (BendingPowerlaw); celerite.terms RealTerm, ComplexTerm,
+ * SHOTerm, Matern32Term, JitterTerm (un-vendored dependency, celerite>=0.4.2). */
+enum mtg_term_kind {
+    MTG_TERM_REAL = 0,        /* log_a, log_c                       -> real (a, c)                     */
+    MTG_TERM_COMPLEX3 = 1,    /* log_a, log_c, log_d                -> complex (a, 0, c, d)            */
+    MTG_TERM_COMPLEX4 = 2,    /* log_a, log_b, log_c, log_d         -> complex (a, b, c, d)            */
+    MTG_TERM_SHO = 3,         /* log_S0, log_Q, log_omega0          -> complex (Q>=1/2) or 2 real      */
+    MTG_TERM_MATERN32 = 4,    /* log_sigma, log_rho ; extra = eps   -> complex                         */
+    MTG_TERM_JITTER = 5,      /* log_sigma                          -> diagonal e^{2 log_sigma}        */
+    MTG_TERM_DRW = 6,         /* log_S0, log_omega0                 -> real (S0, w0)                   */
+    MTG_TERM_LORENTZIAN = 7,  /* log_S0, log_Q, log_omega0          -> complex (S0,0,w0/2Q,w0) + real (0,0) */
+    MTG_TERM_COSINUS = 8,     /* log_S0, log_omega0                 -> complex (S0, 0, 0, w0)          */
+    MTG_TERM_BENDINGPL = 9    /* log_S0, log_Q, log_omega0          -> complex (S0, Q, w0, w0); prior -inf if log_S0 < log_Q */
+};
+
+/* Mean models (mind_the_gaps/gpmodelling.py:62-124, models/mean_models.py:6-31). */
+enum mtg_mean_kind {
+    MTG_MEAN_CONSTANT = 0,    /* value                                        */
+    MTG_MEAN_LINEAR = 1,      /* slope, intercept                             */
+    MTG_MEAN_GAUSSIAN = 2     /* mean, sigma, amplitude, constant             */
+};
+
+/* A GP model: the kernel term list, the mean model and the frozen/free parameter split of
+ * celerite.GP (kernel parameters first, then mean parameters).  Passed BY POINTER from host
+ * memory; the library copies it into kernel arguments. */
+typedef struct mtg_model {
+    int32_t n_terms;
+    int32_t kind[MTG_MAX_TERMS];
+    int32_t pidx[MTG_MAX_TERMS][4];     /* index of each term parameter in the FULL vector   */
+    double  extra[MTG_MAX_TERMS];       /* Matern32 eps                                       */
+    int32_t mean_kind;
+    int32_t mean_pidx[4];               /* indices of the mean parameters in the FULL vector  */
+    int32_t n_full;                     /* kernel + mean parameters, frozen included          */
+    double  full_default[MTG_MAX_PARAMS];/* value of every parameter (used for frozen ones)   */
+    int32_t n_free;                     /* ndim of the sampler / optimiser                    */
+    int32_t free_idx[MTG_MAX_PARAMS];   /* free slot k -> index in the FULL vector            */
+    double  lo[MTG_MAX_PARAMS];         /* box prior on free slot k (-inf / +inf = None)      */
+    double  hi[MTG_MAX_PARAMS];
+} mtg_model_t;
+
+/* flags for mtg_loglike_* / mtg_grad_* */
+#define MTG_FLAG_APPLY_PRIOR   1u  /* add celerite log_prior (box, BendingPowerlaw): out = -inf outside  (gpmodelling.py:147-152) */
+#define MTG_FLAG_DS_MEAN       2u  /* residual = y - ds_mean[data set] (mean frozen at mean(y), gpmodelling.py:83-87)            */
+
+/* ---- library / device ------------------------------------------------------------------ */
+int         mtg_version(void);
+const char *mtg_last_error(void);
+int         mtg_device_count(void);
+int         mtg_set_device(int device);
+/* Width of the celerite recursion the library will run for `model`:
+ * J = Jr + 2 Jc as celerite counts it (j_celerite) and after dropping zero-amplitude real
+ * terms that cannot influence the result (j_compute). */
+int mtg_model_width(const mtg_model_t *model, int *j_celerite, int *j_compute);
+
+/* ---- K1: batched log-likelihood ---------------------------------------------------------
+ * Replaces, for B parameter sets at once, celerite.GP.set_parameter_vector + log_prior +
+ * log_likelihood as called from GPModelling._log_probability (gpmodelling.py:127-152) and
+ * GPModelling._neg_log_like (:155-169); i.e. celerite CholeskySolver.compute + dot_solve +
+ * log_determinant fused into one pass.
+ *   out_ll[B]   log-likelihood (+ log-prior with MTG_FLAG_APPLY_PRIOR); -inf when status != 0
+ *   status[B]   may be NULL
+ *   ds_mean[S]  only read with MTG_FLAG_DS_MEAN                                             */
+int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group, int B,
+                    const double *t, const double *y, const double *diag, const double *ds_mean,
+                    const double *params, double *out_ll, int32_t *status,
+                    uint32_t flags, void *stream);
+/* Host-buffer form.  y/diag are the natural numpy layout here: SERIES-major [S][N]; the
+ * library transposes on the device. */
+int mtg_loglike_host(const mtg_model_t *model, int N, int S, int group, int B,
+                     const double *t, const double *y_sn, const double *diag_sn, const double *ds_mean,
+                     const double *params, double *out_ll, int32_t *status, uint32_t flags);
+
+/* ---- K2: log-likelihood + gradient (fused forward + reverse sweep) ----------------------
+ * New capability (the reference differentiates by scipy finite differences inside
+ * scipy.optimize.minimize(method="L-BFGS-B"), gpmodelling.py:192-193).
+ *   out_grad[B][ndim]  d loglike / d free parameter                                        */
+int mtg_loglike_grad_dev(const mtg_model_t *model, int N, int S, int group, int B,
+                         const double *t, const double *y, const double *diag, const double *ds_mean,
+                         const double *params, double *out_ll, double *out_grad, int32_t *status,
+                         uint32_t flags, void *stream);
+int mtg_loglike_grad_host(const mtg_model_t *model, int N, int S, int group, int B,
+                          const double *t, const double *y_sn, const double *diag_sn, const double *ds_mean,
+                          const double *params, double *out_ll, double *out_grad, int32_t *status,
+                          uint32_t flags);
+
+/* ---- K4: batched box-constrained L-BFGS maximum-likelihood fits -------------------------
+ * Replaces scipy.optimize.minimize(_neg_log_like, x0, method="L-BFGS-B", bounds=...) of
+ * GPModelling.fit (gpmodelling.py:172-194) for B independent problems in lock step.
+ * Bounds come from model->lo / model->hi.
+ *   x0[B][ndim] start points; out_x[B][ndim]; out_nll[B] = -loglike at out_x;
+ *   out_iters[B] (may be NULL); status[B]: 0 converged, 1 iteration limit, 2 failed.       */
+typedef struct mtg_lbfgs_opts {
+    int32_t max_iter;     /* scipy default 15000; typical 200                */
+    int32_t history;      /* m, scipy default 10; <= 10                      */
+    double  ftol;         /* relative f decrease, scipy 2.2e-9               */
+    double  gtol;         /* projected-gradient inf-norm, scipy 1e-5         */
+    int32_t max_ls;       /* line-search evaluations per iteration, scipy 20 */
+    int32_t reserved;
+} mtg_lbfgs_opts_t;
+int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, int B,
+                  const double *t, const double *y, const double *diag, const double *ds_mean,
+                  const double *x0, const mtg_lbfgs_opts_t *opts,
+                  double *out_x, double *out_nll, int32_t *out_iters, int32_t *status,
+                  uint32_t flags, void *stream);
+int mtg_lbfgs_host(const mtg_model_t *model, int N, int S, int group, int B,
+                   const double *t, const double *y_sn, const double *diag_sn, const double *ds_mean,
+                   const double *x0, const mtg_lbfgs_opts_t *opts,
+                   double *out_x, double *out_nll, int32_t *out_iters, int32_t *status, uint32_t flags);
+
+/* ---- pinned host memory -----------------------------------------------------------------
+ * Page-locked buffers for the *_host entry points (cudaMallocHost / cudaFreeHost). */
+int mtg_host_alloc(void **ptr, uint64_t bytes);
+int mtg_host_free(void *ptr);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Dependent-free DFMA microbenchmark: returns achieved FP64 TFLOP/s (2 flop per FMA) on the
+ * current device, timed with CUDA events.  Used by bench.py as the FP64 roofline denominator. */
+int mtg_fp64_peak_probe(double *out_tflops, double *out_ms);
+/* Writes `bytes` of device memory (L2 flush between timed iterations). */
+int mtg_l2_flush(void *scratch_dev, uint64_t bytes, void *stream);
+/* number of kernel launches issued by this library since load (bench.py gpu_launches claim) */
+uint64_t mtg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTG_B200_H */

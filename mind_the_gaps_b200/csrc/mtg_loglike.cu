@@ -1,0 +1,248 @@
+// mtg_loglike.cu -- K1: batched celerite log-likelihood, one thread per series (sm_100a).
+//
+// Replaces celerite CholeskySolver.compute + dot_solve + log_determinant (un-vendored C++), as
+// reached from mind_the_gaps/gpmodelling.py:54, :147-152 (_log_probability), :168-169
+// (_neg_log_like).  The factor, forward-solve and log-determinant passes of celerite are fused
+// into ONE sweep over the N observations: only (S, f, W, D, z) of the previous step are live, so
+// the whole state (J(J+1)/2 + 2J + O(1) doubles) stays in registers and nothing O(N) is stored.
+//
+// Memory plan: the time array (and, when one lightcurve is shared by the batch, rates and
+// variances too) is staged through shared memory in 256-step tiles by TMA bulk copies
+// (cp.async.bulk + mbarrier, double buffered); every thread then reads the same smem word
+// (broadcast, conflict free).  Per-data-set rates/variances are read straight from the
+// time-major [N][S] arrays: a warp touches <= 32 consecutive doubles per step (coalesced) and the
+// next step's values are prefetched one step ahead.
+#include "mtg_common.cuh"
+
+#define K1_THREADS 128
+#define K1_TILE 256
+
+template <int J> __device__ __forceinline__ constexpr int tri(int j, int k)   // j <= k, upper triangle
+{ return j * J - (j * (j - 1)) / 2 + (k - j); }
+
+template <int JR, int JC, bool DUAL>
+struct K1State {
+    static constexpr int J = JR + 2 * JC;
+    static constexpr int NS = J * (J + 1) / 2;
+    double S[NS > 0 ? NS : 1];
+    double f[J > 0 ? J : 1], W[J > 0 ? J : 1];
+    double Dp, zp, tp;          // previous D, z, t
+    double chi2, prod; int esum; bool bad;
+
+    __device__ __forceinline__ void init(double t0)
+    {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) S[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) { f[j] = 0.0; W[j] = 0.0; }
+        Dp = 0.0; zp = 0.0; tp = t0; chi2 = 0.0; prod = 1.0; esum = 0; bad = false;
+    }
+
+    // one observation: (tn, residual rn, diagonal dn).  With the zero-initialised state and
+    // tp = t0 the same code performs the n = 0 start-up (S = 0, f = 0, D = diag + sum a).
+    __device__ __forceinline__ void step(const Coef<JR, JC, DUAL> &c, double tn, double rn, double dn, int n)
+    {
+        const double dt = tn - tp;
+        tp = tn;
+        double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
+#pragma unroll
+        for (int j = 0; j < JR; ++j) { p[j] = exp(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+            const double e = exp(c.ncc[j] * dt);
+            if (!DUAL || c.pair[j]) {
+                double sd, cd;
+                sincos(c.dc[j] * tn, &sd, &cd);
+                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
+                u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd);
+                u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
+                v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
+            } else {
+                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = exp(c.nc2[j] * dt);
+                u[JR + 2 * j] = c.ac[j]; u[JR + 2 * j + 1] = c.a2[j];
+                v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
+            }
+        }
+        // S <- (phi phi^T) o (S + D W W^T)   [previous D, W];   f <- phi o (f + W z)
+        double dw[J > 0 ? J : 1];
+#pragma unroll
+        for (int j = 0; j < J; ++j) dw[j] = Dp * W[j];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int k = j; k < J; ++k)
+                S[tri<J>(j, k)] = (p[j] * p[k]) * fma(dw[j], W[k], S[tri<J>(j, k)]);
+            f[j] = p[j] * fma(W[j], zp, f[j]);
+        }
+        // D = diag + sum a - u^T S u ;  W = (v - S u)/D ;  z = r - u^T f
+        double D = dn + c.a_sum, z = rn;
+        double su[J > 0 ? J : 1];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) acc = fma(S[j <= k ? tri<J>(j, k) : tri<J>(k, j)], u[k], acc);
+            su[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) { D = fma(-u[j], su[j], D); z = fma(-u[j], f[j], z); }
+        const double rD = 1.0 / D;
+#pragma unroll
+        for (int j = 0; j < J; ++j) W[j] = (v[j] - su[j]) * rD;
+        chi2 = fma(z * z, rD, chi2);
+        bad = bad || !(D > 0.0);
+        // sum log D as the log of a running product, renormalised every 4 steps
+        prod *= D;
+        if ((n & 3) == 3) { int e; prod = frexp(prod, &e); esum += e; }
+        Dp = D; zp = z;
+    }
+
+    __device__ __forceinline__ double loglike(int N, int *st) const
+    {
+        const double logdet = log(prod) + (double)esum * 0.6931471805599453094;
+        double ll = -0.5 * (chi2 + logdet + (double)N * 1.8378770664093454836);
+        int s = 0;
+        if (bad) s = 1; else if (!isfinite(ll)) s = 2;
+        if (s) ll = -INFINITY;
+        *st = s;
+        return ll;
+    }
+};
+
+// SHARED: S == 1, rates/variances staged through smem with the times.
+template <int JR, int JC, bool DUAL, bool SHARED>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
+{
+    constexpr int NARR = SHARED ? 3 : 1;
+    __shared__ alignas(128) double sm[2][NARR][K1_TILE];
+    __shared__ alignas(8) uint64_t bar[2];
+
+    const int tid = threadIdx.x;
+    const int b_raw = blockIdx.x * K1_THREADS + tid;
+    const bool valid = b_raw < a.B;
+    const int b = valid ? b_raw : a.B - 1;
+    const int N = a.N;
+    const int ntiles = (N + K1_TILE - 1) / K1_TILE;
+    const bool aligned = ((((uintptr_t)a.t) & 15) == 0) &&
+                         (!SHARED || (((((uintptr_t)a.y) | ((uintptr_t)a.diag)) & 15) == 0));
+    auto tile_count = [&](int k) { return min(K1_TILE, N - k * K1_TILE); };
+    auto use_bulk = [&](int k) { return aligned && ((tile_count(k) & 1) == 0); };
+    auto issue = [&](int k) {      // one thread
+        const int st = k & 1, cnt = tile_count(k);
+        const uint32_t bytes = (uint32_t)cnt * 8u;
+        mbar_expect_tx(&bar[st], bytes * NARR);
+        bulk_g2s(&sm[st][0][0], a.t + (size_t)k * K1_TILE, bytes, &bar[st]);
+        if (SHARED) {
+            bulk_g2s(&sm[st][1][0], a.y + (size_t)k * K1_TILE, bytes, &bar[st]);
+            bulk_g2s(&sm[st][2][0], a.diag + (size_t)k * K1_TILE, bytes, &bar[st]);
+        }
+    };
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        if (use_bulk(0)) issue(0);
+        if (ntiles > 1 && use_bulk(1)) issue(1);
+    }
+
+    // per-series set-up (overlaps the first bulk copies)
+    const double *x = a.params + (size_t)b * pl.n_free;
+    Coef<JR, JC, DUAL> c;
+    plan_coefficients<JR, JC, DUAL>(pl, x, c);
+    const bool inside = !(a.flags & MTG_FLAG_APPLY_PRIOR) || plan_in_prior(pl, x);
+    const int ds = b / a.group;
+    const bool ds_mean = (a.flags & MTG_FLAG_DS_MEAN) != 0;
+    MeanEval mean = plan_mean(pl, x);
+    if (ds_mean) { mean.kind = MTG_MEAN_CONSTANT; mean.p0 = a.ds_mean[ds]; }
+    const double *yp = a.y + ds, *dp = a.diag + ds;
+    const size_t S = (size_t)a.S;
+
+    K1State<JR, JC, DUAL> s;
+    s.init(__ldg(a.t));
+    double y_nx = 0.0, d_nx = 0.0;
+    if (!SHARED) { y_nx = __ldg(yp); d_nx = __ldg(dp); }
+
+    uint32_t phase[2] = {0u, 0u};
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k & 1, cnt = tile_count(k), n0 = k * K1_TILE;
+        if (use_bulk(k)) { mbar_wait(&bar[st], phase[st]); phase[st] ^= 1u; }
+        else {
+            for (int i = tid; i < cnt; i += K1_THREADS) {
+                sm[st][0][i] = a.t[n0 + i];
+                if (SHARED) { sm[st][1][i] = a.y[n0 + i]; sm[st][2][i] = a.diag[n0 + i]; }
+            }
+            __syncthreads();
+        }
+        const double *st_t = &sm[st][0][0];
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) {
+            const int n = n0 + i;
+            const double tn = st_t[i];
+            double yn, dn;
+            if (SHARED) { yn = sm[st][1][i]; dn = sm[st][2][i]; }
+            else {
+                yn = y_nx; dn = d_nx;
+                if (n + 1 < N) { y_nx = __ldg(yp + (size_t)(n + 1) * S); d_nx = __ldg(dp + (size_t)(n + 1) * S); }
+            }
+            s.step(c, tn, yn - mean(tn), dn, n);
+        }
+        __syncthreads();                       // every thread is done with stage st
+        if (tid == 0 && k + 2 < ntiles && use_bulk(k + 2)) { fence_proxy_async(); issue(k + 2); }
+    }
+
+    int stt;
+    double ll = s.loglike(N, &stt);
+    if (!inside) { ll = -INFINITY; stt = 3; }
+    if (valid) {
+        a.out_ll[b] = ll;
+        if (a.status) a.status[b] = stt;
+    }
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------
+template <int JR, int JC>
+static int launch_k1(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
+{
+    const dim3 grid((a.B + K1_THREADS - 1) / K1_THREADS), block(K1_THREADS);
+    const bool shared = (a.S == 1);
+    if (pl.has_sho) {
+        if (shared) k1_loglike<JR, JC, true, true><<<grid, block, 0, stream>>>(pl, a);
+        else        k1_loglike<JR, JC, true, false><<<grid, block, 0, stream>>>(pl, a);
+    } else {
+        if (shared) k1_loglike<JR, JC, false, true><<<grid, block, 0, stream>>>(pl, a);
+        else        k1_loglike<JR, JC, false, false><<<grid, block, 0, stream>>>(pl, a);
+    }
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k1_loglike launch");
+}
+
+#define K1_CASE(R, C) if (pl.jr == R && pl.jc == C) return launch_k1<R, C>(pl, a, stream);
+
+int mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
+{
+    K1_CASE(1, 0) K1_CASE(2, 0) K1_CASE(3, 0)
+    K1_CASE(0, 1) K1_CASE(1, 1) K1_CASE(2, 1) K1_CASE(3, 1)
+    K1_CASE(0, 2) K1_CASE(1, 2) K1_CASE(2, 2)
+    K1_CASE(0, 3) K1_CASE(1, 3) K1_CASE(2, 3)
+    K1_CASE(0, 4) K1_CASE(1, 4)
+    mtg_set_error("unsupported kernel structure: %d real + %d complex recursion slots", pl.jr, pl.jc);
+    return MTG_EUNSUP;
+}
+
+extern "C" int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group, int B,
+                               const double *t, const double *y, const double *diag, const double *ds_mean,
+                               const double *params, double *out_ll, int32_t *status,
+                               uint32_t flags, void *stream)
+{
+    if (!model || N < 1 || S < 1 || group < 1 || B < 0 || !t || !y || !diag || !params || !out_ll) {
+        mtg_set_error("mtg_loglike_dev: bad argument"); return MTG_EINVAL;
+    }
+    if ((flags & MTG_FLAG_DS_MEAN) && !ds_mean) { mtg_set_error("MTG_FLAG_DS_MEAN without ds_mean"); return MTG_EINVAL; }
+    if ((long long)(B - 1) / group >= S && B > 0) { mtg_set_error("B/group exceeds the number of data sets S"); return MTG_EINVAL; }
+    if (B == 0) return 0;
+    Plan pl;
+    int rc = mtg_build_plan(model, &pl);
+    if (rc) return rc;
+    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, nullptr, status, flags};
+    return mtg_k1_dispatch(pl, a, (cudaStream_t)stream);
+}

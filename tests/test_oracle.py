@@ -1,0 +1,91 @@
+"""CPU tests pinning the oracle (no GPU): recursion vs dense Cholesky, the PSD identities the
+reference pins in tests/models_test.py, the C restatement vs numpy."""
+import numpy as np
+import pytest
+
+from oracle import cref, gp, terms
+
+from helpers import fake_lightcurve, c2_truth
+
+
+SPECS = [
+    ([("drw",)], [np.log(0.01), np.log(1e-6)]),
+    ([("drw",), ("lorentzian",)], list(c2_truth())),
+    ([("complex3",), ("real",)], [-6.0, -16.0, -11.8, -6.0, -13.0]),
+    ([("sho",), ("sho",), ("sho",), ("real",)], [-6, 1.0, -12.0, -7, 0.5, -11.0, -8, 2.0, -10.5, -6.0, -14.0]),
+    ([("sho",), ("jitter",)], [-6.0, np.log(0.2), -12.0, -4.0]),
+    ([("matern32", 0.01), ("real",)], [-2.0, 13.0, -6.0, -13.0]),
+    ([("bendingpl",), ("cosinus",)], [-5.0, -7.0, -12.0, -8.0, -11.0]),
+    ([("complex4",)], [-5.0, -8.0, -12.0, -12.5]),
+]
+
+
+@pytest.mark.parametrize("spec,p0", SPECS)
+def test_recursion_matches_dense(spec, p0):
+    t, y, dy, _ = fake_lightcurve(300, 11)
+    rng = np.random.default_rng(5)
+    p = np.asarray(p0)[None, :] + rng.normal(0, 0.05, (3, len(p0)))
+    a = gp.loglike_params(spec, p, t, y, dy)
+    b = gp.loglike_params(spec, p, t, y, dy, dense=True)
+    assert np.all(np.isfinite(b))
+    np.testing.assert_allclose(a, b, rtol=1e-11)
+
+
+def test_c_restatement_matches_numpy():
+    t, y, dy, _ = fake_lightcurve(500, 3)
+    spec = [("drw",), ("lorentzian",)]
+    p = c2_truth()[None, :] + np.random.default_rng(0).normal(0, 0.1, (64, 5))
+    a = cref.loglike_params(spec, p, t, y, dy)
+    b = gp.loglike_params(spec, p, t, y, dy)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+
+
+def test_complex_step_gradient_matches_central_differences():
+    t, y, dy, _ = fake_lightcurve(200, 4)
+    spec = [("drw",), ("lorentzian",)]
+    p = c2_truth()[None, :]
+    g = gp.grad_complex_step(spec, p, t, y, dy)
+    eps = 1e-6
+    for k in range(5):
+        pp = p.copy(); pp[:, k] += eps
+        pm = p.copy(); pm[:, k] -= eps
+        fd = (gp.loglike_params(spec, pp, t, y, dy) - gp.loglike_params(spec, pm, t, y, dy)) / (2 * eps)
+        assert abs(fd[0] - g[0, k]) <= 1e-5 * max(1.0, abs(g[0, k]))
+
+
+def test_not_positive_definite_is_minus_inf():
+    t, y, dy, _ = fake_lightcurve(100, 4)
+    # complex term with b >> a violates a c >= b d
+    ll = gp.loglike_params([("complex4",)], [[-5.0, 3.0, -12.0, -11.0]], t, y, dy)
+    assert ll[0] == -np.inf
+    assert gp.loglike_params([("complex4",)], [[-5.0, 3.0, -12.0, -11.0]], t, y, dy, dense=True)[0] == -np.inf
+
+
+# ---- PSD identities pinned by the reference (tests/models_test.py:14-102, 6 decimals) ------------
+
+def test_psd_drw_equals_bending_powerlaw():
+    w = np.arange(1, 1000)
+    np.testing.assert_array_almost_equal(terms.psd_bendingpowerlaw(w, S0=10, omega0=5, Q=0.5),
+                                         terms.psd([("drw",)], [np.log(10), np.log(5)], w))
+
+
+@pytest.mark.parametrize("Q", [10, 1, 1 / np.sqrt(2), 0.1])
+def test_psd_sho(Q):
+    w = np.arange(1, 1000)
+    np.testing.assert_array_almost_equal(terms.psd_sho(w, S0=10, Q=Q, omega0=5),
+                                         terms.psd([("sho",)], [np.log(10), np.log(Q), np.log(5)], w))
+
+
+@pytest.mark.parametrize("rho", [1, 10, 20])
+def test_psd_matern32(rho):
+    w = np.arange(1, 1000)
+    np.testing.assert_array_almost_equal(terms.psd_matern32(w, sigma=10, rho=rho),
+                                         terms.psd([("matern32", 1e-15)], [np.log(10), np.log(rho)], w))
+
+
+@pytest.mark.parametrize("Q", [1, 10, 100])
+@pytest.mark.parametrize("S0", [1, 10, 100])
+def test_psd_lorentzian(Q, S0):
+    w = np.arange(1, 1000)
+    np.testing.assert_array_almost_equal(terms.psd_lorentzian(w, S0=S0, Q=Q, omega0=5),
+                                         terms.psd([("lorentzian",)], [np.log(S0), np.log(Q), np.log(5)], w))
