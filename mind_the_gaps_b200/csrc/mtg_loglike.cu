@@ -12,102 +12,10 @@
 // (broadcast, conflict free).  Per-data-set rates/variances are read straight from the
 // time-major [N][S] arrays: a warp touches <= 32 consecutive doubles per step (coalesced) and the
 // next step's values are prefetched one step ahead.
-#include "mtg_common.cuh"
+#include "mtg_recursion.cuh"
 
 #define K1_THREADS 128
 #define K1_TILE 256
-
-template <int J> __device__ __forceinline__ constexpr int tri(int j, int k)   // j <= k, upper triangle
-{ return j * J - (j * (j - 1)) / 2 + (k - j); }
-
-template <int JR, int JC, bool DUAL>
-struct K1State {
-    static constexpr int J = JR + 2 * JC;
-    static constexpr int NS = J * (J + 1) / 2;
-    double S[NS > 0 ? NS : 1];
-    double f[J > 0 ? J : 1], W[J > 0 ? J : 1];
-    double Dp, zp, tp;          // previous D, z, t
-    double chi2, prod; int esum; bool bad;
-
-    __device__ __forceinline__ void init(double t0)
-    {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) S[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < J; ++j) { f[j] = 0.0; W[j] = 0.0; }
-        Dp = 0.0; zp = 0.0; tp = t0; chi2 = 0.0; prod = 1.0; esum = 0; bad = false;
-    }
-
-    // one observation: (tn, residual rn, diagonal dn).  With the zero-initialised state and
-    // tp = t0 the same code performs the n = 0 start-up (S = 0, f = 0, D = diag + sum a).
-    __device__ __forceinline__ void step(const Coef<JR, JC, DUAL> &c, double tn, double rn, double dn, int n)
-    {
-        const double dt = tn - tp;
-        tp = tn;
-        double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
-#pragma unroll
-        for (int j = 0; j < JR; ++j) { p[j] = exp(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
-#pragma unroll
-        for (int j = 0; j < JC; ++j) {
-            const double e = exp(c.ncc[j] * dt);
-            if (!DUAL || c.pair[j]) {
-                double sd, cd;
-                sincos(c.dc[j] * tn, &sd, &cd);
-                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
-                u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd);
-                u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
-                v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
-            } else {
-                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = exp(c.nc2[j] * dt);
-                u[JR + 2 * j] = c.ac[j]; u[JR + 2 * j + 1] = c.a2[j];
-                v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
-            }
-        }
-        // S <- (phi phi^T) o (S + D W W^T)   [previous D, W];   f <- phi o (f + W z)
-        double dw[J > 0 ? J : 1];
-#pragma unroll
-        for (int j = 0; j < J; ++j) dw[j] = Dp * W[j];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-#pragma unroll
-            for (int k = j; k < J; ++k)
-                S[tri<J>(j, k)] = (p[j] * p[k]) * fma(dw[j], W[k], S[tri<J>(j, k)]);
-            f[j] = p[j] * fma(W[j], zp, f[j]);
-        }
-        // D = diag + sum a - u^T S u ;  W = (v - S u)/D ;  z = r - u^T f
-        double D = dn + c.a_sum, z = rn;
-        double su[J > 0 ? J : 1];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < J; ++k) acc = fma(S[j <= k ? tri<J>(j, k) : tri<J>(k, j)], u[k], acc);
-            su[j] = acc;
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) { D = fma(-u[j], su[j], D); z = fma(-u[j], f[j], z); }
-        const double rD = 1.0 / D;
-#pragma unroll
-        for (int j = 0; j < J; ++j) W[j] = (v[j] - su[j]) * rD;
-        chi2 = fma(z * z, rD, chi2);
-        bad = bad || !(D > 0.0);
-        // sum log D as the log of a running product, renormalised every 4 steps
-        prod *= D;
-        if ((n & 3) == 3) { int e; prod = frexp(prod, &e); esum += e; }
-        Dp = D; zp = z;
-    }
-
-    __device__ __forceinline__ double loglike(int N, int *st) const
-    {
-        const double logdet = log(prod) + (double)esum * 0.6931471805599453094;
-        double ll = -0.5 * (chi2 + logdet + (double)N * 1.8378770664093454836);
-        int s = 0;
-        if (bad) s = 1; else if (!isfinite(ll)) s = 2;
-        if (s) ll = -INFINITY;
-        *st = s;
-        return ll;
-    }
-};
 
 // SHARED: S == 1, rates/variances staged through smem with the times.
 template <int JR, int JC, bool DUAL, bool SHARED>
