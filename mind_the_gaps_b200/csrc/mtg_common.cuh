@@ -45,6 +45,8 @@ struct BatchArgs {
     const double *t, *y, *diag, *ds_mean, *params;
     double *out_ll; double *out_grad; int32_t *status;
     uint32_t flags;
+    const int32_t *index;   // optional active list: series id of work item i (K2 / L-BFGS)
+    const int32_t *count;   // optional device-side number of work items (<= launch bound)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -180,6 +182,11 @@ __device__ __forceinline__ void fence_proxy_async()
 #endif  // __CUDACC__
 
 // ---- host-side helpers ---------------------------------------------------------------------
+int    mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);
+size_t mtg_k2_tape_bytes_per_series(const Plan &pl, int N);
+int    mtg_k2_chunk(const Plan &pl, int N, int B);
+// a.B work items (series a.index[i] when a.index != NULL, limited to *a.count when a.count != NULL)
+int    mtg_k2_run(const Plan &pl, const BatchArgs &a, double *tape, int chunk, cudaStream_t stream);
 void mtg_set_error(const char *fmt, ...);
 int  mtg_cuda_check(cudaError_t e, const char *what);
 void mtg_count_launch(uint64_t n = 1);

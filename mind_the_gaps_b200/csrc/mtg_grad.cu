@@ -98,7 +98,8 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
     constexpr int K = NS + 2 * J + 2;                       // tape doubles per step: S, f, W, D, z
     const int lb = blockIdx.x * K2_THREADS + threadIdx.x;   // index inside the chunk
     if (lb >= Bc) return;
-    const int b = b0 + lb;
+    if (a.count && b0 + lb >= *a.count) return;
+    const int b = a.index ? a.index[b0 + lb] : b0 + lb;
     const int N = a.N;
     const double *x = a.params + (size_t)b * pl.n_free;
     Coef<JR, JC, DUAL> c;
@@ -384,7 +385,7 @@ extern "C" int mtg_loglike_grad_dev(const mtg_model_t *model, int N, int S, int 
     const int chunk = mtg_k2_chunk(pl, N, B);
     double *tape = nullptr;
     MTG_CUDA(cudaMallocAsync((void **)&tape, mtg_k2_tape_bytes_per_series(pl, N) * (size_t)chunk, stream));
-    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, out_grad, status, flags};
+    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, out_grad, status, flags, nullptr, nullptr};
     rc = mtg_k2_run(pl, a, tape, chunk, stream);
     cudaError_t e = cudaFreeAsync(tape, stream);
     if (rc) return rc;

@@ -1,5 +1,311 @@
+// mtg_lbfgs.cu -- K4: batched, box-constrained L-BFGS maximum-likelihood fits on the device.
+//
+// Replaces scipy.optimize.minimize(self._neg_log_like, x0, method="L-BFGS-B", bounds=...) of
+// GPModelling.fit (mind_the_gaps/gpmodelling.py:172-194) for B independent problems (the null and
+// alternative fits of every simulated lightcurve of the LRT, times their multi-starts).
+//
+// Structure: every problem is a small state machine kept in SoA device arrays.  One ROUND =
+//   (1) K2 evaluates -loglike and its gradient at the trial point of every still-active problem
+//       (one thread per problem, active list compacted in order with cub::DeviceSelect);
+//   (2) k_lbfgs_update advances each problem: Armijo test -> accept (history update, convergence
+//       tests, new two-loop direction with a projected-gradient active set) or shrink the step.
+// The host only launches rounds and reads the active count every few rounds.
+//
+// Differences from scipy's L-BFGS-B (Byrd-Lu-Nocedal-Zhu): the generalised-Cauchy-point /
+// subspace-minimisation step is replaced by a projected L-BFGS direction (variables at a bound with
+// the gradient pointing outwards are frozen for the iteration) and the More-Thuente line search by
+// Armijo backtracking with quadratic interpolation and cautious (s.y > 0) updates.  Stopping tests
+// are scipy's: projected-gradient inf-norm <= gtol, relative decrease <= ftol.  Gradients are
+// analytic (K2) instead of 2-point finite differences.
 #include "mtg_common.cuh"
-extern "C" int mtg_lbfgs_dev(const mtg_model_t *, int, int, int, int, const double *, const double *,
-                             const double *, const double *, const double *, const mtg_lbfgs_opts_t *,
-                             double *, double *, int32_t *, int32_t *, uint32_t, void *)
-{ mtg_set_error("mtg_lbfgs_dev: not built yet"); return MTG_EUNSUP; }
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#define LB_THREADS 128
+#define LB_MAXM 10
+
+struct LbfgsState {
+    int B, nd, m;
+    double *X, *G, *Dir;          // [nd][B]
+    double *SH, *YH;              // [m][nd][B]
+    double *RHO;                  // [m][B]
+    double *F, *alpha, *gd;       // [B]
+    int32_t *hist_n, *hist_head, *ls_count, *iter, *phase, *status, *restarted;   // [B]
+    double *XT, *LL, *GT;         // [B][nd], [B], [B][nd]   K2 input / outputs
+    int32_t *k2_status;           // [B]
+    int32_t *flags;               // [B] 1 = still active
+};
+
+struct LbfgsParams {
+    int max_iter, max_ls; double ftol, gtol, max_step;
+    int nd; double lo[MTG_MAX_PARAMS], hi[MTG_MAX_PARAMS];
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__global__ void k_lbfgs_init(LbfgsState s, LbfgsParams p, const double *__restrict__ x0, int32_t *list)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    for (int k = 0; k < p.nd; ++k) s.XT[(size_t)b * p.nd + k] = clampd(x0[(size_t)b * p.nd + k], p.lo[k], p.hi[k]);
+    s.phase[b] = 0; s.status[b] = 1; s.iter[b] = 0; s.hist_n[b] = 0; s.hist_head[b] = 0; s.ls_count[b] = 0;
+    s.restarted[b] = 0; s.flags[b] = 1; s.F[b] = INFINITY; s.alpha[b] = 1.0; s.gd[b] = 0.0;
+    list[b] = b;
+}
+
+// new search direction at the current point; returns false if the point is stationary
+__device__ bool lbfgs_direction(const LbfgsState &s, const LbfgsParams &p, int b, double *alpha_out)
+{
+    const int nd = p.nd, B = s.B;
+    double q[MTG_MAX_PARAMS], g[MTG_MAX_PARAMS];
+    bool fixed[MTG_MAX_PARAMS];
+    double qq = 0.0;
+    for (int k = 0; k < nd; ++k) {
+        const double xk = s.X[(size_t)k * B + b];
+        g[k] = s.G[(size_t)k * B + b];
+        fixed[k] = (xk <= p.lo[k] && g[k] > 0.0) || (xk >= p.hi[k] && g[k] < 0.0);
+        q[k] = fixed[k] ? 0.0 : g[k];
+        qq += q[k] * q[k];
+    }
+    if (!(qq > 0.0)) return false;
+    int hn = s.hist_n[b];
+    const int head = s.hist_head[b];       // slot of the NEXT write; newest = head-1
+    double al[LB_MAXM];
+    double d[MTG_MAX_PARAMS];
+    for (int k = 0; k < nd; ++k) d[k] = q[k];
+    for (int i = 0; i < hn; ++i) {
+        const int slot = (head - 1 - i + 2 * s.m) % s.m;
+        double sd = 0.0;
+        for (int k = 0; k < nd; ++k) if (!fixed[k]) sd += s.SH[((size_t)slot * nd + k) * B + b] * d[k];
+        al[i] = s.RHO[(size_t)slot * B + b] * sd;
+        for (int k = 0; k < nd; ++k) if (!fixed[k]) d[k] -= al[i] * s.YH[((size_t)slot * nd + k) * B + b];
+    }
+    if (hn > 0) {
+        const int slot = (head - 1 + s.m) % s.m;
+        double sy = 0.0, yy = 0.0;
+        for (int k = 0; k < nd; ++k) if (!fixed[k]) {
+            const double yk = s.YH[((size_t)slot * nd + k) * B + b];
+            sy += s.SH[((size_t)slot * nd + k) * B + b] * yk; yy += yk * yk;
+        }
+        const double gamma = (yy > 0.0 && sy > 0.0) ? sy / yy : 1.0;
+        for (int k = 0; k < nd; ++k) d[k] *= gamma;
+    }
+    for (int i = hn - 1; i >= 0; --i) {
+        const int slot = (head - 1 - i + 2 * s.m) % s.m;
+        double yd = 0.0;
+        for (int k = 0; k < nd; ++k) if (!fixed[k]) yd += s.YH[((size_t)slot * nd + k) * B + b] * d[k];
+        const double be = s.RHO[(size_t)slot * B + b] * yd;
+        for (int k = 0; k < nd; ++k) if (!fixed[k]) d[k] += (al[i] - be) * s.SH[((size_t)slot * nd + k) * B + b];
+    }
+    double gdir = 0.0;
+    for (int k = 0; k < nd; ++k) { d[k] = fixed[k] ? 0.0 : -d[k]; gdir += g[k] * d[k]; }
+    if (!(gdir < 0.0) || !isfinite(gdir)) {          // not a descent direction: steepest descent restart
+        hn = 0; s.hist_n[b] = 0;
+        gdir = 0.0;
+        for (int k = 0; k < nd; ++k) { d[k] = -q[k]; gdir += g[k] * d[k]; }
+    }
+    double alpha = (hn == 0) ? fmin(1.0, 1.0 / sqrt(qq)) : 1.0;
+    double dmax = 0.0;
+    for (int k = 0; k < nd; ++k) dmax = fmax(dmax, fabs(d[k]));
+    if (alpha * dmax > p.max_step) alpha = p.max_step / dmax;
+    for (int k = 0; k < nd; ++k) s.Dir[(size_t)k * B + b] = d[k];
+    s.gd[b] = gdir;
+    *alpha_out = alpha;
+    return true;
+}
+
+__device__ __forceinline__ void lbfgs_set_trial(const LbfgsState &s, const LbfgsParams &p, int b, double alpha)
+{
+    const int nd = p.nd, B = s.B;
+    s.alpha[b] = alpha;
+    for (int k = 0; k < nd; ++k)
+        s.XT[(size_t)b * nd + k] = clampd(s.X[(size_t)k * B + b] + alpha * s.Dir[(size_t)k * B + b], p.lo[k], p.hi[k]);
+}
+
+__global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__restrict__ list,
+                               const int32_t *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const int b = list[i];
+    const int nd = p.nd, B = s.B;
+    double ft = -s.LL[b];
+    if (s.k2_status[b] != 0 || !isfinite(ft)) ft = INFINITY;
+    double gt[MTG_MAX_PARAMS], xt[MTG_MAX_PARAMS];
+    for (int k = 0; k < nd; ++k) { gt[k] = -s.GT[(size_t)b * nd + k]; xt[k] = s.XT[(size_t)b * nd + k]; }
+    bool done = false; int status = 1;
+    bool need_dir = false;
+
+    if (s.phase[b] == 0) {
+        if (!isfinite(ft)) { done = true; status = 2; for (int k = 0; k < nd; ++k) s.X[(size_t)k * B + b] = xt[k]; s.F[b] = ft; }
+        else {
+            for (int k = 0; k < nd; ++k) { s.X[(size_t)k * B + b] = xt[k]; s.G[(size_t)k * B + b] = gt[k]; }
+            s.F[b] = ft; s.phase[b] = 1; need_dir = true;
+        }
+    } else {
+        const double F = s.F[b];
+        double gdx = 0.0, ss = 0.0, yy = 0.0, sy = 0.0;
+        double dx[MTG_MAX_PARAMS], dg[MTG_MAX_PARAMS];
+        for (int k = 0; k < nd; ++k) {
+            const double gk = s.G[(size_t)k * B + b];
+            dx[k] = xt[k] - s.X[(size_t)k * B + b]; dg[k] = gt[k] - gk;
+            gdx += gk * dx[k]; ss += dx[k] * dx[k]; yy += dg[k] * dg[k]; sy += dx[k] * dg[k];
+        }
+        if (isfinite(ft) && ft <= F + 1e-4 * gdx) {
+            // accept the step
+            if (sy > 1e-10 * sqrt(ss) * sqrt(yy) && sy > 0.0) {
+                const int slot = s.hist_head[b];
+                for (int k = 0; k < nd; ++k) { s.SH[((size_t)slot * nd + k) * B + b] = dx[k]; s.YH[((size_t)slot * nd + k) * B + b] = dg[k]; }
+                s.RHO[(size_t)slot * B + b] = 1.0 / sy;
+                s.hist_head[b] = (slot + 1) % s.m;
+                if (s.hist_n[b] < s.m) s.hist_n[b] += 1;
+            }
+            double pg = 0.0;
+            for (int k = 0; k < nd; ++k) {
+                s.X[(size_t)k * B + b] = xt[k]; s.G[(size_t)k * B + b] = gt[k];
+                pg = fmax(pg, fabs(xt[k] - clampd(xt[k] - gt[k], p.lo[k], p.hi[k])));
+            }
+            s.F[b] = ft;
+            const int it = s.iter[b] + 1; s.iter[b] = it;
+            s.restarted[b] = 0;
+            if (pg <= p.gtol) { done = true; status = 0; }
+            else if ((F - ft) <= p.ftol * fmax(fmax(fabs(F), fabs(ft)), 1.0)) { done = true; status = 0; }
+            else if (it >= p.max_iter) { done = true; status = 1; }
+            else need_dir = true;
+        } else {
+            const int lc = s.ls_count[b] + 1; s.ls_count[b] = lc;
+            if (lc >= p.max_ls) {
+                if (s.hist_n[b] > 0 && !s.restarted[b]) { s.hist_n[b] = 0; s.restarted[b] = 1; need_dir = true; }
+                else { done = true; status = 2; }
+            } else {
+                const double a0 = s.alpha[b], gd = s.gd[b];
+                double an = 0.25 * a0;
+                if (isfinite(ft)) {
+                    const double den = 2.0 * (ft - F - gd * a0);
+                    if (den > 0.0) an = -gd * a0 * a0 / den;
+                    an = fmin(fmax(an, 0.1 * a0), 0.5 * a0);
+                }
+                lbfgs_set_trial(s, p, b, an);
+            }
+        }
+    }
+    if (need_dir) {
+        double alpha;
+        if (!lbfgs_direction(s, p, b, &alpha)) { done = true; status = 0; }
+        else { s.ls_count[b] = 0; lbfgs_set_trial(s, p, b, alpha); }
+    }
+    if (done) { s.status[b] = status; s.flags[b] = 0; }
+}
+
+__global__ void k_lbfgs_finish(LbfgsState s, double *__restrict__ out_x, double *__restrict__ out_nll,
+                               int32_t *__restrict__ out_iters, int32_t *__restrict__ out_status)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    for (int k = 0; k < s.nd; ++k) out_x[(size_t)b * s.nd + k] = s.X[(size_t)k * s.B + b];
+    out_nll[b] = s.F[b];
+    if (out_iters) out_iters[b] = s.iter[b];
+    if (out_status) out_status[b] = s.status[b];        // still-active problems keep 1 (iteration limit)
+}
+
+extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, int B,
+                             const double *t, const double *y, const double *diag, const double *ds_mean,
+                             const double *x0, const mtg_lbfgs_opts_t *opts,
+                             double *out_x, double *out_nll, int32_t *out_iters, int32_t *out_status,
+                             uint32_t flags, void *stream_)
+{
+    if (!model || N < 1 || S < 1 || group < 1 || B < 0 || !t || !y || !diag || !x0 || !out_x || !out_nll) {
+        mtg_set_error("mtg_lbfgs_dev: bad argument"); return MTG_EINVAL;
+    }
+    if ((flags & MTG_FLAG_DS_MEAN) && !ds_mean) { mtg_set_error("MTG_FLAG_DS_MEAN without ds_mean"); return MTG_EINVAL; }
+    if (B > 0 && (long long)(B - 1) / group >= S) { mtg_set_error("B/group exceeds the number of data sets S"); return MTG_EINVAL; }
+    if (B == 0) return 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Plan pl;
+    int rc = mtg_build_plan(model, &pl);
+    if (rc) return rc;
+    const int nd = pl.n_free;
+    if (nd < 1) { mtg_set_error("mtg_lbfgs_dev: the model has no free parameters"); return MTG_EINVAL; }
+    LbfgsParams p;
+    p.max_iter = opts && opts->max_iter > 0 ? opts->max_iter : 200;
+    p.max_ls = opts && opts->max_ls > 0 ? opts->max_ls : 20;
+    p.ftol = opts && opts->ftol > 0 ? opts->ftol : 2.220446049250313e-09;
+    p.gtol = opts && opts->gtol > 0 ? opts->gtol : 1e-5;
+    p.max_step = 8.0;
+    p.nd = nd;
+    for (int k = 0; k < nd; ++k) { p.lo[k] = pl.lo[k]; p.hi[k] = pl.hi[k]; }
+    int m = opts && opts->history > 0 ? opts->history : 10;
+    if (m > LB_MAXM) m = LB_MAXM;
+
+    // ---- one allocation for all state ---------------------------------------------------------
+    const size_t Bz = (size_t)B;
+    size_t nd_ = (size_t)nd;
+    size_t n_dbl = 3 * nd_ * Bz + 2 * (size_t)m * nd_ * Bz + (size_t)m * Bz + 3 * Bz + 2 * nd_ * Bz + Bz;
+    size_t n_int = 9 * Bz + 2 * Bz + 8;
+    size_t cub_bytes = 0;
+    cub::CountingInputIterator<int32_t> iota(0);
+    cub::DeviceSelect::Flagged((void *)nullptr, cub_bytes, iota, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, B, stream);
+    const size_t total = n_dbl * 8 + n_int * 4 + cub_bytes + 1024;
+    char *base = nullptr;
+    MTG_CUDA(cudaMallocAsync((void **)&base, total, stream));
+    double *dptr = (double *)base;
+    auto take_d = [&](size_t n) { double *r = dptr; dptr += n; return r; };
+    LbfgsState s;
+    s.B = B; s.nd = nd; s.m = m;
+    s.X = take_d(nd_ * Bz); s.G = take_d(nd_ * Bz); s.Dir = take_d(nd_ * Bz);
+    s.SH = take_d((size_t)m * nd_ * Bz); s.YH = take_d((size_t)m * nd_ * Bz); s.RHO = take_d((size_t)m * Bz);
+    s.F = take_d(Bz); s.alpha = take_d(Bz); s.gd = take_d(Bz);
+    s.XT = take_d(nd_ * Bz); s.GT = take_d(nd_ * Bz); s.LL = take_d(Bz);
+    int32_t *iptr = (int32_t *)dptr;
+    auto take_i = [&](size_t n) { int32_t *r = iptr; iptr += n; return r; };
+    s.hist_n = take_i(Bz); s.hist_head = take_i(Bz); s.ls_count = take_i(Bz); s.iter = take_i(Bz);
+    s.phase = take_i(Bz); s.status = take_i(Bz); s.restarted = take_i(Bz); s.k2_status = take_i(Bz); s.flags = take_i(Bz);
+    int32_t *list_a = take_i(Bz), *list_b = take_i(Bz);
+    int32_t *d_count = take_i(8);           // [0], [1]: ping-pong counts
+    void *cub_tmp = (void *)(((uintptr_t)iptr + 255) & ~(uintptr_t)255);
+
+    const int chunk = mtg_k2_chunk(pl, N, B);
+    double *tape = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&tape, mtg_k2_tape_bytes_per_series(pl, N) * (size_t)chunk, stream);
+    if (e != cudaSuccess) { cudaFreeAsync(base, stream); return mtg_cuda_check(e, "cudaMallocAsync(tape)"); }
+    int32_t *h_count = nullptr;
+    e = cudaMallocHost((void **)&h_count, sizeof(int32_t));
+    if (e != cudaSuccess) { cudaFreeAsync(tape, stream); cudaFreeAsync(base, stream); return mtg_cuda_check(e, "cudaMallocHost"); }
+
+    const dim3 blk(LB_THREADS);
+    k_lbfgs_init<<<(B + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, p, x0, list_a);
+    *h_count = B;
+    cudaMemcpyAsync(d_count, h_count, sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+    mtg_count_launch();
+
+    int bound = B;                          // host-side upper bound on the active count
+    int32_t *list = list_a, *list_next = list_b;
+    int32_t *cnt = d_count, *cnt_next = d_count + 1;
+    const long long max_rounds = (long long)p.max_iter * (p.max_ls + 1) + 2;
+    rc = 0;
+    for (long long round = 0; round < max_rounds && bound > 0; ++round) {
+        BatchArgs a{N, S, group, bound, t, y, diag, ds_mean, s.XT, s.LL, s.GT, s.k2_status, flags, list, cnt};
+        if ((rc = mtg_k2_run(pl, a, tape, chunk, stream))) break;
+        k_lbfgs_update<<<(bound + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, p, list, cnt);
+        // ordered compaction of the still-active problems
+        size_t tmp_bytes = cub_bytes;
+        cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, iota, s.flags, list_next, cnt_next, B, stream);
+        mtg_count_launch(2);
+        { int32_t *sw = list; list = list_next; list_next = sw; sw = cnt; cnt = cnt_next; cnt_next = sw; }
+        if ((round & 3) == 3 || bound <= 4096) {
+            cudaMemcpyAsync(h_count, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+            if ((rc = mtg_cuda_check(cudaStreamSynchronize(stream), "lbfgs round sync"))) break;
+            bound = *h_count;
+        }
+    }
+    if (!rc) {
+        k_lbfgs_finish<<<(B + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, out_x, out_nll, out_iters, out_status);
+        mtg_count_launch();
+        rc = mtg_cuda_check(cudaGetLastError(), "lbfgs finish");
+    }
+    cudaFreeAsync(tape, stream);
+    cudaFreeAsync(base, stream);
+    if (!rc) rc = mtg_cuda_check(cudaStreamSynchronize(stream), "lbfgs final sync");
+    cudaFreeHost(h_count);
+    return rc;
+}
