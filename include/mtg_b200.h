@@ -161,6 +161,85 @@ int mtg_lbfgs_host(const mtg_model_t *model, int N, int S, int group, int B,
                    const double *x0, const mtg_lbfgs_opts_t *opts,
                    double *out_x, double *out_nll, int32_t *out_iters, int32_t *status, uint32_t flags);
 
+
+/* ---- simulator (K3 spectrum synthesis, cuFFT Z2D, K5 segment + exposure binning, K6 E13, K7 noise)
+ * Replaces Simulator.generate_lightcurve + add_noise (mind_the_gaps/simulator.py:369-420, 300-338;
+ * noise_models.py) for L lightcurves at once.  A simulator object owns the observing window
+ * (Simulator.__init__, simulator.py:195-258): the regular grid, the bin edges ("strategy"), the
+ * exposures / backgrounds, cuFFT plans and chunk buffers. */
+enum mtg_pdf_kind   { MTG_PDF_GAUSSIAN = 0, MTG_PDF_LOGNORMAL = 1, MTG_PDF_UNIFORM = 2 };
+enum mtg_noise_kind { MTG_NOISE_POISSON = 0, MTG_NOISE_KRAFT = 1, MTG_NOISE_GAUSSIAN = 2 };
+
+typedef struct mtg_sim_config {
+    int32_t n_obs;              /* N observation bins                                              */
+    int32_t n_fft;              /* len(sim_timestamps)            (simulator.py:234-238)           */
+    double  sim_dt;             /* min(exposures)/aliasing_factor (simulator.py:217)               */
+    double  sim_duration;       /* length of the random segment   (simulator.py:226-228)           */
+    double  mean;               /* target mean count rate                                          */
+    int32_t pdf;                /* mtg_pdf_kind: Gaussian -> TK95, else E13 (simulator.py:207-214) */
+    int32_t max_iter;           /* E13 iterations (default 400)                                    */
+    int32_t noise;              /* mtg_noise_kind                 (simulator.py:245-251)           */
+    int32_t reserved;
+    double  sigma_noise;        /* Gaussian noise sigma                                            */
+    double  kraft_counts;       /* Kraft threshold, 15            (noise_models.py:87)             */
+    const double *grid;         /* host [n_fft]  sim_timestamps exactly as np.arange produced them */
+    const double *bin_lo;       /* host [n_obs]  strategy[i][0]   (simulator.py:254-255)           */
+    const double *bin_hi;       /* host [n_obs]  strategy[i][1]                                    */
+    const double *exposures;    /* host [n_obs]                                                    */
+    const double *bkg_counts;   /* host [n_obs] or NULL (zeros): bkg_rate * exposures              */
+    const double *bkg_rate_err; /* host [n_obs] or NULL (zeros)                                    */
+} mtg_sim_config_t;
+
+int mtg_sim_create(const mtg_sim_config_t *cfg, void **sim);
+int mtg_sim_destroy(void *sim);
+
+/* Generate L noiseless binned lightcurves.
+ * PSD source: `model` + params[L][n_free] (celerite kernel PSD evaluated on the device, the
+ * generate_from_posteriors path gpmodelling.py:533-536) OR psd_table[n_fft/2+1] = psd(rfftfreq*2pi)
+ * evaluated by the caller for an arbitrary callable (one PSD for all L).
+ * Random inputs: Philox4x32-10 streams keyed by `seed` unless the caller injects them
+ * (parity tests): normals[L][2][n_fft/2+1] (the two rows of simulator.py:492), u_segment[L] (the
+ * random_sample() behind np.random.uniform, simulator.py:538), pdf_normals[L][n_seg_max]
+ * (standard normal / uniform(0,1) variates turned into pdf.rvs draws, simulator.py:90).
+ *   out_rates[L][n_obs]   (host form)  /  out_rates_tm[n_obs][L] time-major (device form)
+ *   out_seg[L][2]         first index and length of the random segment (may be NULL)            */
+int mtg_sim_generate_host(void *sim, int L, const mtg_model_t *model, const double *params,
+                          const double *psd_table, uint64_t seed,
+                          const double *normals, const double *u_segment, const double *pdf_variates,
+                          double *out_rates, int32_t *out_seg, int32_t *out_e13_iters);
+int mtg_sim_generate_dev(void *sim, int L, const mtg_model_t *model, const double *params_dev,
+                         const double *psd_table_dev, uint64_t seed,
+                         double *out_rates_tm, void *stream);
+/* Add noise and estimate uncertainties (noise_models.py).  counts_in[L][n_obs] (the
+ * np.random.poisson draws) / normals_in[L][n_obs] inject the randomness for parity tests.
+ * status[L][n_obs]: 0 ok, 1 negative expected counts (numpy raises ValueError("lam < 0")).     */
+int mtg_sim_add_noise_host(void *sim, int L, const double *rates, uint64_t seed,
+                           const int64_t *counts_in, const double *normals_in,
+                           double *out_rates, double *out_dy, int32_t *status);
+int mtg_sim_add_noise_dev(void *sim, int L, const double *rates_tm, uint64_t seed,
+                          double *out_rates_tm, double *out_dy_tm, void *stream);
+
+/* PoissonNoise / KraftNoise / GaussianNoise.add_noise (noise_models.py:49-184) on explicit host arrays:
+ * rates[L][n_obs]; exposures / bkg_counts / bkg_rate_err [n_obs] (the last two may be NULL = zeros). */
+int mtg_noise_host(int kind, int L, int n_obs, const double *rates, const double *exposures,
+                   const double *bkg_counts, const double *bkg_rate_err, double sigma, double kraft_counts,
+                   uint64_t seed, const int64_t *counts_in, const double *normals_in,
+                   double *out_rates, double *out_dy, int32_t *status);
+/* Simulator.simulate_regularly_sampled (simulator.py:369-394): the full-resolution TK95 count rates
+ * out_countrate[L][n_fft] (mean included), same PSD sources / injected normals as generate. */
+int mtg_sim_regular_host(void *sim, int L, const mtg_model_t *model, const double *params,
+                         const double *psd_table, uint64_t seed, const double *normals, double *out_countrate);
+
+/* Simulator.downsample (simulator.py:340-367) on explicit arrays: per-bin np.mean of countrate over
+ * {j : time[j] >= lo && time[j] < hi}, summed in numpy's pairwise order (bit-exact), plus the index
+ * range of every bin.  time must be non-decreasing.                                              */
+int mtg_downsample_host(int n_seg, const double *time, const double *countrate, int n_obs,
+                        const double *bin_lo, const double *bin_hi,
+                        double *out_rates, int32_t *out_first, int32_t *out_count);
+/* E13Simulator.adjust_lightcurve_pdf (simulator.py:65-131) for one lightcurve on explicit draws. */
+int mtg_e13_adjust_host(int n, const double *countrate, const double *xsim0, int max_iter,
+                        double *out_x, int32_t *out_iters);
+
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers for the *_host entry points (cudaMallocHost / cudaFreeHost). */
 int mtg_host_alloc(void **ptr, uint64_t bytes);

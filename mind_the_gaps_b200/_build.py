@@ -18,6 +18,10 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas"
               "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
 
 
+# the simulator restates NumPy expressions whose index results must match bit for bit: no FMA contraction
+EXTRA_FLAGS = {"mtg_sim.cu": ["-fmad=false"]}
+
+
 def nvcc():
     for cand in (os.environ.get("MTG_NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
         if cand and os.path.exists(cand):
@@ -42,7 +46,7 @@ def _compile(src, verbose):
     headers.append(os.path.join(CSRC, "..", "..", "include", "mtg_b200.h"))
     if not _stale(obj, [os.path.join(CSRC, src)] + headers):
         return obj, ""
-    cmd = [nvcc()] + ARCH + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc()] + ARCH + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, p.stdout))

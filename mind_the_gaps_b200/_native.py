@@ -47,6 +47,20 @@ class MtgLbfgsOpts(ctypes.Structure):
                 ("gtol", ctypes.c_double), ("max_ls", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class MtgSimConfig(ctypes.Structure):
+    """``mtg_sim_config_t``"""
+    _fields_ = [("n_obs", ctypes.c_int32), ("n_fft", ctypes.c_int32), ("sim_dt", ctypes.c_double),
+                ("sim_duration", ctypes.c_double), ("mean", ctypes.c_double), ("pdf", ctypes.c_int32),
+                ("max_iter", ctypes.c_int32), ("noise", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("sigma_noise", ctypes.c_double), ("kraft_counts", ctypes.c_double),
+                ("grid", ctypes.c_void_p), ("bin_lo", ctypes.c_void_p), ("bin_hi", ctypes.c_void_p),
+                ("exposures", ctypes.c_void_p), ("bkg_counts", ctypes.c_void_p), ("bkg_rate_err", ctypes.c_void_p)]
+
+
+PDF_GAUSSIAN, PDF_LOGNORMAL, PDF_UNIFORM = 0, 1, 2
+NOISE_POISSON, NOISE_KRAFT, NOISE_GAUSSIAN = 0, 1, 2
+
+
 class MtgError(RuntimeError):
     pass
 
@@ -78,6 +92,17 @@ SIGNATURES = {
     "mtg_lbfgs_host": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(MtgLbfgsOpts),
                                       _vp, _vp, _vp, _vp, ctypes.c_uint32]),
+    "mtg_sim_create": (ctypes.c_int, [ctypes.POINTER(MtgSimConfig), ctypes.POINTER(ctypes.c_void_p)]),
+    "mtg_sim_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mtg_sim_generate_host": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_sim_generate_dev": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
+    "mtg_sim_add_noise_host": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_sim_add_noise_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
+    "mtg_noise_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_sim_regular_host": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
+    "mtg_downsample_host": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_e13_adjust_host": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp]),
     "mtg_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "mtg_host_free": (ctypes.c_int, [_vp]),
     "mtg_fp64_peak_probe": (ctypes.c_int, [_dp, _dp]),
