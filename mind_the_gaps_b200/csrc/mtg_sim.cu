@@ -173,11 +173,13 @@ __device__ double np_pairwise_sum(const double *a, int n)
     n2 -= n2 % 8;
     return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
 }
-// np.mean of a contiguous 1-D slice: np.add.reduce = a[0] + pairwise(a[1:]), then / n
+// np.mean of the fancy-indexed (k, 1) slice the reference averages (simulator.py:362-364): numpy's
+// add.reduce is the pairwise sum over all k elements, then a true divide by k (verified against
+// numpy 2.3 for k = 1..1000 in tests/test_simulator_gpu.py)
 __device__ __forceinline__ double np_mean(const double *a, int n)
 {
     if (n <= 0) return nan("");
-    return (a[0] + np_pairwise_sum(a + 1, n - 1)) / (double)n;
+    return np_pairwise_sum(a, n) / (double)n;
 }
 
 // first j in [0, len) with (time(j) >= x), time(j) = base[j] + shift, starting from a guess
