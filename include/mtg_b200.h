@@ -240,6 +240,17 @@ int mtg_downsample_host(int n_seg, const double *time, const double *countrate, 
 int mtg_e13_adjust_host(int n, const double *countrate, const double *xsim0, int max_iter,
                         double *out_x, int32_t *out_iters);
 
+/* ---- LRT pipeline helpers (device-resident data, time-major [N][S]) -------------------------
+ * diag = (dy + 1e-12)^2 (gpmodelling.py:54) and mean_out[s] = mean_n y[n][s] (gpmodelling.py:83-87). */
+int mtg_prepare_data_dev(int N, int S, const double *y_tm, const double *dy_tm, double *diag_tm,
+                         double *mean_out, void *stream);
+/* best[s] = min over the `group` consecutive problems of data set s (multi-start), arg[s] = its index */
+int mtg_group_best_dev(int S, int group, const double *f, double *best, int32_t *arg, void *stream);
+/* celerite GP.predict(y, return_var=True, return_cov=False) at the training times
+ * (GPModelling.standarized_residuals, gpmodelling.py:353-370) for ONE parameter vector. */
+int mtg_predict_host(const mtg_model_t *model, int N, const double *t, const double *y, const double *diag,
+                     const double *params, double *out_mu, double *out_var);
+
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers for the *_host entry points (cudaMallocHost / cudaFreeHost). */
 int mtg_host_alloc(void **ptr, uint64_t bytes);

@@ -103,6 +103,9 @@ SIGNATURES = {
     "mtg_sim_regular_host": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "mtg_downsample_host": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mtg_e13_adjust_host": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "mtg_prepare_data_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_group_best_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "mtg_predict_host": (ctypes.c_int, [_mp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mtg_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "mtg_host_free": (ctypes.c_int, [_vp]),
     "mtg_fp64_peak_probe": (ctypes.c_int, [_dp, _dp]),

@@ -47,6 +47,7 @@ struct BatchArgs {
     uint32_t flags;
     const int32_t *index;   // optional active list: series id of work item i (K2 / L-BFGS)
     const int32_t *count;   // optional device-side number of work items (<= launch bound)
+    double *per_step;       // optional K2 output [2][N][B]: alpha_n = (K^-1 r)_n and (K^-1)_nn  (GP.predict)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -230,6 +230,10 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
             bf[j] = fma(-bz, u[j], bf[j]);
         }
         g.a_sum += bD;
+        if (a.per_step) {       // d loglike / d r_n = -alpha_n ;  d loglike / d diag_n = 1/2 alpha_n^2 - 1/2 (K^-1)_nn
+            a.per_step[(size_t)n * a.B + b] = -bz;
+            a.per_step[((size_t)N + n) * a.B + b] = fma(bz, bz, -2.0 * bD);
+        }
         // bu += S bsu ; bS += bsu u^T (symmetrised)
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -385,7 +389,7 @@ extern "C" int mtg_loglike_grad_dev(const mtg_model_t *model, int N, int S, int 
     const int chunk = mtg_k2_chunk(pl, N, B);
     double *tape = nullptr;
     MTG_CUDA(cudaMallocAsync((void **)&tape, mtg_k2_tape_bytes_per_series(pl, N) * (size_t)chunk, stream));
-    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, out_grad, status, flags, nullptr, nullptr};
+    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, out_grad, status, flags, nullptr, nullptr, nullptr};
     rc = mtg_k2_run(pl, a, tape, chunk, stream);
     cudaError_t e = cudaFreeAsync(tape, stream);
     if (rc) return rc;

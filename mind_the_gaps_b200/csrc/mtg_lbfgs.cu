@@ -284,7 +284,7 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     const long long max_rounds = (long long)p.max_iter * (p.max_ls + 1) + 2;
     rc = 0;
     for (long long round = 0; round < max_rounds && bound > 0; ++round) {
-        BatchArgs a{N, S, group, bound, t, y, diag, ds_mean, s.XT, s.LL, s.GT, s.k2_status, flags, list, cnt};
+        BatchArgs a{N, S, group, bound, t, y, diag, ds_mean, s.XT, s.LL, s.GT, s.k2_status, flags, list, cnt, nullptr};
         if ((rc = mtg_k2_run(pl, a, tape, chunk, stream))) break;
         k_lbfgs_update<<<(bound + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, p, list, cnt);
         // ordered compaction of the still-active problems

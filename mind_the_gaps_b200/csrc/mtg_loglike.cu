@@ -151,6 +151,6 @@ extern "C" int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group
     Plan pl;
     int rc = mtg_build_plan(model, &pl);
     if (rc) return rc;
-    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, nullptr, status, flags, nullptr, nullptr};
+    BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, nullptr, status, flags, nullptr, nullptr, nullptr};
     return mtg_k1_dispatch(pl, a, (cudaStream_t)stream);
 }

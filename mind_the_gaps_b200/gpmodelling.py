@@ -1,0 +1,262 @@
+"""``GPModelling``: the Gaussian-process modelling interface of mind_the_gaps
+(``/root/reference/mind_the_gaps/gpmodelling.py``) on top of the B200 kernels.
+
+Same constructor, methods, keyword arguments, properties and error behaviour as the reference
+class.  What changed underneath:
+
+* ``self.gp`` is ``mind_the_gaps_b200.celerite.GP`` (K1/K2 kernels) instead of ``celerite.GP``;
+* ``fit`` runs the batched device L-BFGS with analytic gradients (one problem here; the LRT driver
+  hands it thousands) and returns a ``scipy.optimize.OptimizeResult`` like ``scipy.optimize.minimize``;
+* ``derive_posteriors`` evaluates each half-ensemble of the stretch move in ONE kernel launch
+  (``vectorize=True`` seam of emcee) -- ``cores`` is accepted and ignored, there is no process pool;
+* ``generate_from_posteriors`` simulates all ``nsims`` lightcurves in one batched device call
+  (``cpus`` accepted and ignored).
+"""
+import warnings
+
+import numpy as np
+from scipy.optimize import OptimizeResult
+
+from . import fitting
+from .celerite import GP
+from .celerite.modeling import ConstantModel
+from .lightcurves import GappyLightcurve
+from .models import GaussianModel, LinearModel
+from .sampler import EnsembleSampler
+
+__all__ = ["GPModelling"]
+
+
+class GPModelling(object):
+    """The interface for Gaussian Process (GP) modelling."""
+    meanmodels = ["linear", "constant", "gaussian"]
+
+    def __init__(self, lightcurve, kernel, mean_model=None):
+        self._lightcurve = lightcurve
+        meanmodel, fit_mean = self._build_mean_model(mean_model)
+        self.gp = GP(kernel, mean=meanmodel, fit_mean=fit_mean)
+        self.gp.compute(self._lightcurve.times, self._lightcurve.dy + 1e-12)      # gpmodelling.py:54
+        self.initial_params = self.gp.get_parameter_vector()
+        self._ndim = len(self.initial_params)
+        self._autocorr = []
+        self._loglikelihoods = None
+        self._mcmc_samples = None
+        self._sampler = None
+
+    def _build_mean_model(self, meanmodel=None):
+        lc = self._lightcurve
+        maxy = np.max(lc.y)
+        if meanmodel is None:
+            return ConstantModel(lc.mean, bounds=[(np.min(lc.y), maxy)]), False
+        if meanmodel.lower() not in GPModelling.meanmodels:
+            raise ValueError("Input mean model %s not implemented! Only \n %s \n are available"
+                             % (meanmodel, "\t".join(GPModelling.meanmodels)))
+        if meanmodel.lower() == "constant":
+            return ConstantModel(lc.mean, bounds=[(np.min(lc.y), maxy)]), True
+        if meanmodel.lower() == "linear":
+            return LinearModel(0, 1.5, bounds=[(-np.inf, np.inf), (-np.inf, np.inf)]), True
+        # gaussian (gpmodelling.py:114-122).  The reference passes three values for GaussianModel's four
+        # parameter names (a latent bug that raises inside celerite); the missing ``constant`` is started
+        # at the lightcurve mean here.
+        sigma_guess = lc.duration / 2
+        amplitude_guess = (maxy - np.min(lc.y)) * np.sqrt(2 * np.pi) * sigma_guess
+        mean_guess = lc.times[len(lc.times) // 2]
+        amp_lo = maxy * np.sqrt(2 * np.pi) * lc.duration
+        amp_hi = 50 * maxy * np.sqrt(2 * np.pi) * lc.duration
+        amplitude_guess = min(max(amplitude_guess, amp_lo), amp_hi)
+        return GaussianModel(mean_guess, sigma_guess, amplitude_guess, lc.mean,
+                             bounds=[(lc.times[0], lc.times[-1]), (0, lc.duration), (amp_lo, amp_hi),
+                                     (np.min(lc.y), maxy)]), True
+
+    # -- likelihood ----------------------------------------------------------------------------------------
+    def _log_probability(self, params):
+        """log posterior at ``params`` (``(ndim,)``) or at a batch ``(B, ndim)`` -> ``(B,)``."""
+        params = np.asarray(params, dtype=np.float64)
+        if params.ndim == 2:
+            return self.gp.log_probability_batch(self._lightcurve.y, params)
+        self.gp.set_parameter_vector(params)
+        lp = self.gp.log_prior()
+        if not np.isfinite(lp):
+            return -np.inf
+        return lp + self.gp.log_likelihood(self._lightcurve.y)
+
+    def _neg_log_like(self, params):
+        self.gp.set_parameter_vector(params)
+        return -self.gp.log_likelihood(self._lightcurve.y)
+
+    def fit(self, initial_params=None, n_starts=1, **opts):
+        """Maximum-likelihood fit by (device) L-BFGS within ``gp.get_parameter_bounds()``; returns an
+        ``OptimizeResult`` (``x, fun, success, status, message, nit``) like ``scipy.optimize.minimize``."""
+        if initial_params is None:
+            initial_params = self.initial_params
+        lc = self._lightcurve
+        ds_mean = None
+        model = self.gp.device_model()
+        starts = fitting.multistart_points(np.asarray(initial_params, dtype=np.float64), self.gp.get_parameter_bounds(),
+                                           int(n_starts), np.random.default_rng(np.random.randint(0, 2 ** 31 - 1)))
+        res = fitting.lbfgs_batch(model, lc.times, lc.y, lc.dy, starts, int(n_starts), ds_mean=ds_mean, **opts)
+        fun = np.where(np.isfinite(res["fun"]), res["fun"], np.inf)
+        i = int(np.argmin(fun))
+        st = int(res["status"][i])
+        solution = OptimizeResult(x=res["x"][i].copy(), fun=float(res["fun"][i]), nit=int(res["nit"][i]), status=st,
+                                  success=(st == 0), message=fitting._MESSAGES.get(st, "?"))
+        if np.all(np.isfinite(solution.x)):
+            self.gp.set_parameter_vector(solution.x)
+        return solution
+
+    # -- posteriors -----------------------------------------------------------------------------------------
+    def derive_posteriors(self, initial_chain_params=None, fit=True, converge=True, max_steps=10000,
+                          convergence_steps=500, walkers=12, cores=6, progress=True):
+        if initial_chain_params is None:
+            if not fit:
+                initial_params = self.initial_params
+            else:
+                initial_params = self.fit(self.initial_params).x
+            initial_chain_params = self.spread_walkers(walkers, initial_params, np.array(self.gp.get_parameter_bounds()))
+        every_samples = convergence_steps
+        old_tau = np.inf
+        self.converged = False
+        y = self._lightcurve.y
+        sampler = EnsembleSampler(walkers, self._ndim, lambda p: self.gp.log_probability_batch(y, p), vectorize=True)
+        tau = None
+        for sample in sampler.sample(initial_chain_params, iterations=max_steps, progress=progress):
+            if sampler.iteration % every_samples:
+                continue
+            tau = sampler.get_autocorr_time(tol=0)
+            self.autocorr.append(np.mean(tau))
+            if np.all(tau * 100 < sampler.iteration) and np.all(np.abs(old_tau - tau) / tau < 0.01) and converge:
+                print("Convergence reached after %d samples!" % sampler.iteration)
+                self.converged = True
+                break
+            old_tau = tau
+        if tau is None:
+            # the reference hits a NameError here (max_steps < convergence_steps); estimate once instead
+            tau = sampler.get_autocorr_time(tol=0)
+        self._tau = tau
+        mean_tau = np.mean(tau)
+        if not self.converged:
+            warnings.warn(f"The chains did not converge after {sampler.iteration} iterations!")
+            thin = int(mean_tau / 4)
+            discard = int(mean_tau) * 5
+        else:
+            discard = int(mean_tau * 40)
+            if discard > max_steps:
+                discard = int(mean_tau * 10)
+            thin = int(mean_tau / 2)
+        thin = max(thin, 1)                     # the reference passes thin=0 to emcee for tau < 2 (slice error)
+        discard = min(discard, max(sampler.iteration - thin, 0))
+        self._loglikelihoods = sampler.get_log_prob(discard=discard, thin=thin, flat=True)
+        self._mcmc_samples = sampler.get_chain(discard=discard, thin=thin, flat=True)
+        self._sampler = sampler
+
+    def spread_walkers(self, walkers, parameters, bounds, percent=0.1, max_attempts=20):
+        """Gaussian ball around ``parameters`` (sigma = ``percent`` * |parameter|) inside ``bounds``: walkers
+        falling outside are redrawn up to ``max_attempts`` times, then set to 1.05 / 0.95 of the violated
+        bound (gpmodelling.py:289-350)."""
+        if percent < 0 or percent > 1:
+            raise ValueError("The 'percent' parameter must be between 0 and 1 (inclusive).")
+        parameters = np.asarray(parameters, dtype=np.float64)
+        std = np.abs(parameters) * percent
+        initial_samples = np.random.normal(parameters, std, size=(walkers, len(parameters)))
+        bounds = np.array([(-np.inf if lower is None else lower, np.inf if upper is None else upper)
+                           for lower, upper in bounds], dtype=np.float64)
+        factors_lower = np.where(bounds[:, 0] > 0, 1.05, 0.95)
+        factors_upper = np.where(bounds[:, 1] > 0, 0.95, 1.05)
+        inside = lambda v: np.all(np.logical_and(bounds[:, 0] <= v, v <= bounds[:, 1]))
+        for i in range(walkers):
+            attempt = 0
+            for attempt in range(max_attempts):
+                if inside(initial_samples[i]):
+                    break
+                initial_samples[i] = np.random.normal(parameters, std)
+            if attempt == max_attempts - 1:
+                warnings.warn("Some walkers are out of bounds! Setting them to values close to the bounds")
+                low = initial_samples[i] < bounds[:, 0]
+                up = initial_samples[i] > bounds[:, 1]
+                with np.errstate(invalid="ignore"):
+                    initial_samples[i][low] = (bounds[:, 0] * factors_lower)[low]
+                    initial_samples[i][up] = (bounds[:, 1] * factors_upper)[up]
+        return initial_samples
+
+    def standarized_residuals(self, include_noise=True):
+        pred_mean, pred_var = self.gp.predict(self._lightcurve.y, return_var=True, return_cov=False)
+        if include_noise:
+            pred_var += self.gp.kernel.jitter
+        return (self._lightcurve.y - pred_mean) / np.sqrt(pred_var)
+
+    def get_rstat(self, burnin=None):
+        if self._sampler is None:
+            raise ValueError("Posteriors have not been derived. Please run derive_posteriors prior to populate the attributes.")
+        if burnin is None:
+            burnin = int(np.mean(self.tau)) * 10
+        samples = self._sampler.get_chain(discard=burnin)
+        whithin_chain_variances = np.var(samples, axis=0)
+        samples = self._sampler.get_chain(flat=True, discard=burnin)
+        between_chain_variances = np.var(samples, axis=0)
+        return whithin_chain_variances / between_chain_variances[np.newaxis, :]
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def _need(self, value):
+        if value is None:
+            raise AttributeError("Posteriors have not been derived. Please run derive_posteriors prior to populate the attributes.")
+        return value
+
+    @property
+    def loglikelihoods(self):
+        return self._need(self._loglikelihoods)
+
+    @property
+    def autocorr(self):
+        return self._autocorr
+
+    @property
+    def sampler(self):
+        self._need(self._loglikelihoods)
+        return self._sampler
+
+    @property
+    def mcmc_samples(self):
+        return self._need(self._mcmc_samples)
+
+    @property
+    def max_loglikelihood(self):
+        return np.max(self._need(self._loglikelihoods))
+
+    @property
+    def max_parameters(self):
+        return self._need(self._mcmc_samples)[np.argmax(self._loglikelihoods)]
+
+    @property
+    def median_parameters(self):
+        return np.median(self._need(self._mcmc_samples), axis=0)
+
+    @property
+    def parameter_names(self):
+        return self.gp.get_parameter_names()
+
+    @property
+    def k(self):
+        return self._ndim
+
+    @property
+    def tau(self):
+        self._need(self._mcmc_samples)
+        return self._tau
+
+    # -- simulation from the posteriors -------------------------------------------------------------------------
+    def generate_from_posteriors(self, nsims=10, cpus=8, pdf="Gaussian", extension_factor=2, sigma_noise=None):
+        """``nsims`` lightcurves, each simulated from one random posterior sample of the kernel parameters
+        with the observing window, exposures and noise model of the data (gpmodelling.py:478-539)."""
+        if self._mcmc_samples is None:
+            raise RuntimeError("Posteriors have not been derived. Please run derive_posteriors prior to calling this method.")
+        if nsims >= len(self._mcmc_samples):
+            warnings.warn("The number of simulation requested (%d) is higher than the number of posterior samples (%d), "
+                          "so many samples will be drawn more than once" % (nsims, len(self._mcmc_samples)))
+        param_samples = self._mcmc_samples[np.random.randint(len(self._mcmc_samples), size=nsims)]
+        simulator = self._lightcurve.get_simulator(self.gp.kernel.get_psd, pdf, sigma_noise=sigma_noise,
+                                                   extension_factor=extension_factor)
+        nk = self.gp.kernel.vector_size
+        rates = simulator.generate_lightcurves(nsims, parameters=param_samples[:, :nk])
+        noisy, dy = simulator.add_noise(rates)
+        simulator.close()
+        return [GappyLightcurve(self._lightcurve.times, noisy[i], dy[i]) for i in range(nsims)]

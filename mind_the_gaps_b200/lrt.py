@@ -1,0 +1,207 @@
+"""Protassov likelihood-ratio test on the GPU: simulate -> fit null -> fit alternative, batched.
+
+The reference has no library function for this; it is notebook cells
+(``/root/reference/docs/notebooks/tutorial_ppp.ipynb`` cells 11-15): draw posterior samples of the null
+model, ``generate_from_posteriors``, then for every simulated lightcurve fit both models (L-BFGS-B
+followed by a short MCMC whose maximum log-posterior is kept) and form
+``T = -2 (L_null - L_alt)``; ``p = 1 - percentileofscore(T_dist, T_obs) / 100``.
+
+Here every stage stays on the device for a whole shard of simulations: ``mtg_sim_generate_dev`` ->
+``mtg_sim_add_noise_dev`` -> ``mtg_prepare_data_dev`` -> ``mtg_lbfgs_dev`` (null, multi-start) ->
+``mtg_lbfgs_dev`` (alternative, multi-start, one start nested at the null optimum so T >= 0) ->
+``mtg_group_best_dev``.  The per-simulation MCMC refinement of the reference is replaced by
+multi-start MLE (north_star), so agreement with the reference is statistical (distribution of T).
+Simulations are independent: with ``torch.distributed`` initialised they are sharded over the ranks
+(one GPU each) and only ``(T, L_null, L_alt, status)`` are gathered (NCCL all-gather).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .celerite import GP
+from .stats import lrt_pvalue, lrt_statistic
+
+__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts"]
+
+
+class LRTResult(object):
+    def __init__(self, T, loglike_null, loglike_alt, params_null, params_alt, status_null, status_alt, timings=None):
+        self.T = T; self.loglike_null = loglike_null; self.loglike_alt = loglike_alt
+        self.params_null = params_null; self.params_alt = params_alt
+        self.status_null = status_null; self.status_alt = status_alt
+        self.timings = timings or {}
+
+    def pvalue(self, T_obs):
+        return lrt_pvalue(self.T, T_obs)
+
+
+def shard_range(n, rank, world):
+    """Contiguous block of ``n`` items owned by ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(int(n), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _bounds_arrays(gp):
+    b = gp.get_parameter_bounds()
+    lo = np.array([-np.inf if x[0] is None else x[0] for x in b], dtype=np.float64)
+    hi = np.array([np.inf if x[1] is None else x[1] for x in b], dtype=np.float64)
+    return lo, hi
+
+
+def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
+    """Start points of the alternative fits, ``(L, n_starts, nd)``: start 0 is the alternative's initial
+    vector with its null-model components replaced by the null optimum (nested start: the fit can only
+    improve on the null likelihood up to the cost of the extra term), the next third are Gaussian balls
+    around it (10 % as ``spread_walkers``), the rest are uniform inside the finite bounds for the
+    parameters that do not belong to the null model."""
+    L = x_null_best.shape[0]; nd = len(x_alt0)
+    base = np.tile(np.asarray(x_alt0, dtype=np.float64), (L, 1))
+    base[:, null_slots] = x_null_best
+    out = np.repeat(base[:, None, :], n_starts, axis=1)
+    if n_starts > 1:
+        n_ball = max(1, (n_starts - 1) // 3)
+        out[:, 1:1 + n_ball, :] += rng.normal(size=(L, n_ball, nd)) * (0.1 * np.abs(base))[:, None, :]
+        extra = [k for k in range(nd) if k not in set(null_slots)]
+        n_uni = n_starts - 1 - n_ball
+        for k in extra:
+            if n_uni > 0 and np.isfinite(lo[k]) and np.isfinite(hi[k]):
+                out[:, 1 + n_ball:, k] = rng.uniform(lo[k], hi[k], size=(L, n_uni))
+            elif n_uni > 0:
+                out[:, 1 + n_ball:, k] += rng.normal(size=(L, n_uni)) * (0.5 * np.abs(base[:, k]) + 0.5)[:, None]
+    return np.clip(out, lo, hi)
+
+
+def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
+                     extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
+                     max_iter=200, device=None, distributed=None, chunk=4096, return_lightcurves=False):
+    """Simulate one lightcurve per row of ``null_samples`` (posterior draws of the null kernel's
+    parameters) on the window of ``lightcurve`` and MLE-fit each with both kernels.
+
+    ``null_slots``: positions in the alternative's parameter vector of the parameters it shares with the
+    null model (default: the trailing ``len(null)`` ones when the alternative is ``extra + null`` as in the
+    tutorial, else the leading ones if names match).  Returns an ``LRTResult`` holding the arrays for ALL
+    simulations (gathered over ranks when ``torch.distributed`` is initialised)."""
+    import torch
+    lib = _native.lib()
+    _native.require_device()
+    dist = None
+    rank, world = 0, 1
+    if distributed is None:
+        import torch.distributed as tdist
+        if tdist.is_available() and tdist.is_initialized():
+            dist = tdist
+    elif distributed:
+        import torch.distributed as tdist
+        dist = tdist
+    if dist is not None:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    _native.check(lib.mtg_set_device(device.index if device.index is not None else 0))
+
+    null_samples = np.ascontiguousarray(np.atleast_2d(null_samples), dtype=np.float64)
+    n_total = null_samples.shape[0]
+    i0, i1 = shard_range(n_total, rank, world)
+    mine = null_samples[i0:i1]
+    L = mine.shape[0]
+
+    gp0 = GP(null_kernel, mean=0.0); gp1 = GP(alt_kernel, mean=0.0)
+    m0 = gp0.device_model(); m1 = gp1.device_model()
+    nd0, nd1 = m0.n_free, m1.n_free
+    lo0, hi0 = _bounds_arrays(gp0); lo1, hi1 = _bounds_arrays(gp1)
+    if null_slots is None:
+        n0 = list(null_kernel.get_parameter_names()); n1 = list(alt_kernel.get_parameter_names())
+        strip = lambda s: s.split(":")[-1]
+        tail = [strip(s) for s in n1[len(n1) - nd0:]]; head = [strip(s) for s in n1[:nd0]]
+        null_slots = list(range(nd1 - nd0, nd1)) if tail == [strip(s) for s in n0] and head != tail else list(range(nd0))
+    x_alt0 = gp1.get_parameter_vector().copy()
+
+    sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor)
+    h = sim._sim()
+    N = lightcurve.n
+    t_dev = torch.from_numpy(np.ascontiguousarray(lightcurve.times, dtype=np.float64)).to(device)
+    stream = torch.cuda.current_stream(device)
+    sp = stream.cuda_stream
+    rng = np.random.default_rng(seed + 7919 * rank)
+    opts = _native.MtgLbfgsOpts(int(max_iter), 10, 2.220446049250313e-09, 1e-5, 20, 0)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_sim = t_null = t_alt = 0.0
+    out_T = np.empty(L); out_l0 = np.empty(L); out_l1 = np.empty(L)
+    out_p0 = np.empty((L, nd0)); out_p1 = np.empty((L, nd1)); out_s0 = np.empty(L, dtype=np.int32); out_s1 = np.empty(L, dtype=np.int32)
+    kept = []
+    for c0 in range(0, L, chunk):
+        Lc = min(chunk, L - c0)
+        p_dev = torch.from_numpy(np.ascontiguousarray(mine[c0:c0 + Lc])).to(device)
+        rates = torch.empty((N, Lc), dtype=torch.float64, device=device)
+        y = torch.empty_like(rates); dy = torch.empty_like(rates); diag = torch.empty_like(rates)
+        means = torch.empty(Lc, dtype=torch.float64, device=device)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record(stream)
+        _native.check(lib.mtg_sim_generate_dev(h, Lc, ctypes.byref(m0), p_dev.data_ptr(), None,
+                                               int(seed) * 1000003 + (i0 + c0), rates.data_ptr(), sp))
+        _native.check(lib.mtg_sim_add_noise_dev(h, Lc, rates.data_ptr(), int(seed) * 1000003 + 17 + (i0 + c0),
+                                                y.data_ptr(), dy.data_ptr(), sp))
+        _native.check(lib.mtg_prepare_data_dev(N, Lc, y.data_ptr(), dy.data_ptr(), diag.data_ptr(), means.data_ptr(), sp))
+        e1.record(stream)
+        # ---- null fits: start 0 = the generating parameters, others = 10 % Gaussian balls ----------------
+        from .fitting import multistart_points
+        x0 = multistart_points(mine[c0:c0 + Lc], list(zip(lo0, hi0)), n_starts_null, rng)
+        B0 = Lc * n_starts_null
+        x0_dev = torch.from_numpy(np.ascontiguousarray(x0)).to(device)
+        ox = torch.empty((B0, nd0), dtype=torch.float64, device=device); of = torch.empty(B0, dtype=torch.float64, device=device)
+        oi = torch.empty(B0, dtype=torch.int32, device=device); os_ = torch.empty(B0, dtype=torch.int32, device=device)
+        _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m0), N, Lc, n_starts_null, B0, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
+                                        means.data_ptr(), x0_dev.data_ptr(), ctypes.byref(opts), ox.data_ptr(), of.data_ptr(),
+                                        oi.data_ptr(), os_.data_ptr(), _native.FLAG_DS_MEAN, sp))
+        best0 = torch.empty(Lc, dtype=torch.float64, device=device); arg0 = torch.empty(Lc, dtype=torch.int32, device=device)
+        _native.check(lib.mtg_group_best_dev(Lc, n_starts_null, of.data_ptr(), best0.data_ptr(), arg0.data_ptr(), sp))
+        e2.record(stream)
+        a0 = arg0.cpu().numpy().astype(np.int64)
+        x_null = ox.cpu().numpy()[a0]
+        # ---- alternative fits ---------------------------------------------------------------------------------
+        x1 = alternative_starts(x_alt0, x_null, null_slots, lo1, hi1, n_starts_alt, rng).reshape(Lc * n_starts_alt, nd1)
+        B1 = Lc * n_starts_alt
+        x1_dev = torch.from_numpy(np.ascontiguousarray(x1)).to(device)
+        ax = torch.empty((B1, nd1), dtype=torch.float64, device=device); af = torch.empty(B1, dtype=torch.float64, device=device)
+        ai = torch.empty(B1, dtype=torch.int32, device=device); as_ = torch.empty(B1, dtype=torch.int32, device=device)
+        _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m1), N, Lc, n_starts_alt, B1, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
+                                        means.data_ptr(), x1_dev.data_ptr(), ctypes.byref(opts), ax.data_ptr(), af.data_ptr(),
+                                        ai.data_ptr(), as_.data_ptr(), _native.FLAG_DS_MEAN, sp))
+        best1 = torch.empty(Lc, dtype=torch.float64, device=device); arg1 = torch.empty(Lc, dtype=torch.int32, device=device)
+        _native.check(lib.mtg_group_best_dev(Lc, n_starts_alt, af.data_ptr(), best1.data_ptr(), arg1.data_ptr(), sp))
+        e3.record(stream)
+        torch.cuda.synchronize(device)
+        t_sim += e0.elapsed_time(e1); t_null += e1.elapsed_time(e2); t_alt += e2.elapsed_time(e3)
+        a1 = arg1.cpu().numpy().astype(np.int64)
+        sl = slice(c0, c0 + Lc)
+        out_l0[sl] = -best0.cpu().numpy(); out_l1[sl] = -best1.cpu().numpy()
+        out_p0[sl] = x_null; out_p1[sl] = ax.cpu().numpy()[a1]
+        out_s0[sl] = os_.cpu().numpy()[a0]; out_s1[sl] = as_.cpu().numpy()[a1]
+        if return_lightcurves:
+            kept.append((y.cpu().numpy().T.copy(), dy.cpu().numpy().T.copy()))
+    sim.close()
+    out_T[:] = lrt_statistic(out_l0, out_l1)
+    timings = {"simulate_ms": t_sim, "fit_null_ms": t_null, "fit_alt_ms": t_alt, "n_local": L}
+
+    if dist is not None and world > 1:
+        counts = [shard_range(n_total, r, world) for r in range(world)]
+        nmax = max(b - a for a, b in counts)
+        width = 5 + nd0 + nd1
+        pack = np.full((nmax, width), np.nan)
+        pack[:L, 0] = out_T; pack[:L, 1] = out_l0; pack[:L, 2] = out_l1; pack[:L, 3] = out_s0; pack[:L, 4] = out_s1
+        pack[:L, 5:5 + nd0] = out_p0; pack[:L, 5 + nd0:] = out_p1
+        send = torch.from_numpy(pack).to(device)
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        parts = [recv[r].cpu().numpy()[: counts[r][1] - counts[r][0]] for r in range(world)]
+        allp = np.concatenate(parts, axis=0)
+        res = LRTResult(allp[:, 0], allp[:, 1], allp[:, 2], allp[:, 5:5 + nd0], allp[:, 5 + nd0:],
+                        allp[:, 3].astype(np.int32), allp[:, 4].astype(np.int32), timings)
+    else:
+        res = LRTResult(out_T, out_l0, out_l1, out_p0, out_p1, out_s0, out_s1, timings)
+    if return_lightcurves:
+        res.lightcurves = (np.concatenate([k[0] for k in kept]), np.concatenate([k[1] for k in kept])) if kept else None
+    return res

@@ -1,0 +1,161 @@
+"""Affine-invariant ensemble sampler with the slice of the ``emcee`` 3.1.4 API that ``GPModelling``
+uses (``/root/reference/mind_the_gaps/gpmodelling.py:247-264, 284-286, 397-401``):
+``EnsembleSampler(nwalkers, ndim, log_prob_fn, pool=None)``, ``sample(p0, iterations, progress)``,
+``iteration``, ``get_autocorr_time(tol=0)``, ``get_chain / get_log_prob(discard, thin, flat)``.
+
+Algorithm: Goodman & Weare (2010) stretch move, red/blue split as in emcee's ``RedBlueMove`` with
+``nsplits=2`` and ``a=2``: each half of the ensemble is updated against the other half,
+and the whole half is handed to the log-probability function in ONE call -- with
+``vectorize=True`` a ``(B, ndim)`` array goes straight to the batched GPU kernel (B = nwalkers / 2).
+emcee is not importable in this environment; this is a restatement of its published algorithm, not
+a copy, and the random stream differs (NumPy ``Generator`` instead of emcee's ``RandomState``).
+"""
+import numpy as np
+
+__all__ = ["EnsembleSampler", "integrated_time", "AutocorrError"]
+
+
+class AutocorrError(Exception):
+    pass
+
+
+def _next_pow_two(n):
+    i = 1
+    while i < n:
+        i <<= 1
+    return i
+
+
+def _acf_1d(x):
+    n = _next_pow_two(len(x))
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[:len(x)].real
+    return acf / acf[0]
+
+
+def integrated_time(x, c=5, tol=50, quiet=False):
+    """Integrated autocorrelation time per dimension with Sokal's automatic window (emcee
+    ``autocorr.integrated_time``): ``x`` is ``(steps, walkers, ndim)``."""
+    x = np.atleast_1d(x)
+    if x.ndim == 1:
+        x = x[:, None, None]
+    if x.ndim == 2:
+        x = x[:, :, None]
+    n_t, n_w, n_d = x.shape
+    tau = np.empty(n_d)
+    windows = np.empty(n_d, dtype=int)
+    for d in range(n_d):
+        f = np.zeros(n_t)
+        for k in range(n_w):
+            f += _acf_1d(x[:, k, d])
+        f /= n_w
+        taus = 2.0 * np.cumsum(f) - 1.0
+        m = np.arange(len(taus)) < c * taus
+        windows[d] = np.argmin(m) if np.any(~m) else len(taus) - 1
+        tau[d] = taus[windows[d]]
+    if tol > 0 and np.any(tol * tau > n_t) and not quiet:
+        raise AutocorrError("The chain is shorter than %d times the integrated autocorrelation time" % tol)
+    return tau
+
+
+class EnsembleSampler(object):
+    def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, moves=None, args=None, kwargs=None,
+                 vectorize=False, a=2.0, seed=None):
+        if nwalkers < 2 * ndim:
+            raise ValueError("the number of walkers must be at least twice the dimension (got %d for ndim=%d)" % (nwalkers, ndim))
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        self.log_prob_fn = log_prob_fn
+        self.pool = pool
+        self.vectorize = vectorize
+        self.args = args or []
+        self.kwargs = kwargs or {}
+        self.a = float(a)
+        self._rng = np.random.default_rng(seed if seed is not None else np.random.randint(0, 2 ** 31 - 1))
+        self.reset()
+
+    def reset(self):
+        self.iteration = 0
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty((0, self.nwalkers))
+        self._accepted = np.zeros(self.nwalkers)
+
+    # -- log probability of a batch of positions -------------------------------------------------------
+    def compute_log_prob(self, coords):
+        p = np.asarray(coords, dtype=np.float64)
+        if np.any(~np.isfinite(p)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        if self.vectorize:
+            lp = np.asarray(self.log_prob_fn(p, *self.args, **self.kwargs), dtype=np.float64)
+        else:
+            if self.pool is not None:
+                vals = self.pool.map(self.log_prob_fn, list(p))
+            else:
+                vals = [self.log_prob_fn(q, *self.args, **self.kwargs) for q in p]
+            lp = np.array([float(v) for v in vals], dtype=np.float64)
+        if np.any(np.isnan(lp)):
+            raise ValueError("Probability function returned NaN")
+        return lp
+
+    def _grow(self, n):
+        self._chain = np.concatenate([self._chain, np.empty((n, self.nwalkers, self.ndim))], axis=0)
+        self._log_prob = np.concatenate([self._log_prob, np.empty((n, self.nwalkers))], axis=0)
+
+    def sample(self, initial_state, iterations=1, progress=False, store=True):
+        p = np.array(initial_state, dtype=np.float64)
+        if p.shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions %r" % (p.shape,))
+        if self.nwalkers > 1 and np.linalg.cond(np.atleast_2d(np.cov(p, rowvar=False))) > 1e8:
+            raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent "
+                             "for the best performance")
+        lp = self.compute_log_prob(p)
+        if store:
+            self._grow(int(iterations))
+        nw, nd = self.nwalkers, self.ndim
+        for _ in range(int(iterations)):
+            perm = self._rng.permutation(nw)
+            halves = [perm[: nw // 2], perm[nw // 2:]]
+            for h in range(2):
+                S, C = halves[h], halves[1 - h]
+                ns = len(S)
+                zz = ((self.a - 1.0) * self._rng.random(ns) + 1.0) ** 2 / self.a
+                partner = p[C[self._rng.integers(len(C), size=ns)]]
+                q = partner - (partner - p[S]) * zz[:, None]
+                lq = self.compute_log_prob(q)
+                with np.errstate(invalid="ignore"):
+                    lnpdiff = (nd - 1.0) * np.log(zz) + lq - lp[S]
+                accept = np.log(self._rng.random(ns)) < lnpdiff
+                idx = S[accept]
+                p[idx] = q[accept]
+                lp[idx] = lq[accept]
+                self._accepted[idx] += 1
+            if store:
+                self._chain[self.iteration] = p
+                self._log_prob[self.iteration] = lp
+            self.iteration += 1
+            yield p, lp
+
+    def run_mcmc(self, initial_state, nsteps, **kwargs):
+        out = None
+        for out in self.sample(initial_state, iterations=nsteps, **kwargs):
+            pass
+        return out
+
+    # -- results ---------------------------------------------------------------------------------------------
+    def _get(self, arr, discard, thin, flat):
+        v = arr[: self.iteration][discard + thin - 1:: thin]
+        if flat:
+            return v.reshape((-1,) + v.shape[2:])
+        return v
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self._get(self._chain, int(discard), int(thin), flat)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        return self._get(self._log_prob, int(discard), int(thin), flat)
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
+
+    @property
+    def acceptance_fraction(self):
+        return self._accepted / max(self.iteration, 1)

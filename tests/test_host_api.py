@@ -1,0 +1,175 @@
+"""CPU tests of the host-side mirror of the reference API.  They restate the reference's own tests
+(tests/gpmodelling_test.py, tests/models_test.py, tests/stats_test.py) against this package."""
+import warnings
+
+import numpy as np
+import pytest
+
+from mind_the_gaps_b200.celerite import GP, terms
+from mind_the_gaps_b200.gpmodelling import GPModelling
+from mind_the_gaps_b200.lightcurves import GappyLightcurve
+from mind_the_gaps_b200.models import BendingPowerlaw, DampedRandomWalk, Lorentzian, celerite_models, psd_models
+from mind_the_gaps_b200 import stats as mstats
+from mind_the_gaps_b200.sampler import EnsembleSampler, integrated_time
+
+
+def _gpmodel(bounds_drw, bounds_lor, lor_params=(10, 5, -5), drw_params=(5.0, 10.0)):
+    kernel = DampedRandomWalk(drw_params[0], drw_params[1], bounds=bounds_drw) + \
+        Lorentzian(lor_params[0], lor_params[1], lor_params[2], bounds=bounds_lor)
+    lc = GappyLightcurve(np.arange(100), np.arange(100), np.arange(100))
+    return GPModelling(lc, kernel)
+
+
+# ---- tests/gpmodelling_test.py ---------------------------------------------------------------------------
+
+def test_parameters_within_bounds():
+    bounds_drw = [(4.0, 6.0), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+    parameters = [5.0, 10.0, 10, 5, -5]
+    bounds = bounds_drw + bounds_lor
+    for percent, attempts in ((0.1, 100), (0.9, 2)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            samples = gpmodel.spread_walkers(100, parameters, bounds, percent=percent, max_attempts=attempts)
+        for i, sample in enumerate(samples.T):
+            assert np.all(np.logical_and(bounds[i][0] <= sample, sample <= bounds[i][1]))
+
+
+def test_infinite_bounds():
+    bounds_drw = [(None, None), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+    bounds = bounds_drw + bounds_lor
+    samples = gpmodel.spread_walkers(100, [5.0, 10.0, 10, 5, -5], bounds, percent=0.1, max_attempts=50)
+    assert np.all(np.isfinite(samples[:, 0]))
+    for b, sample in zip(bounds[1:], samples.T[1:]):
+        assert np.all(np.logical_and(b[0] <= sample, sample <= b[1]))
+
+
+def test_percent_zero_gives_exact_parameters():
+    bounds_drw = [(4.0, 6.0), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+    parameters = [5.0, 10.0, 10, 5, -5]
+    samples = gpmodel.spread_walkers(50, parameters, bounds_drw + bounds_lor, percent=0.0)
+    assert np.array_equal(samples, np.tile(parameters, (50, 1)))
+    with pytest.raises(ValueError):
+        gpmodel.spread_walkers(5, parameters, bounds_drw + bounds_lor, percent=1.5)
+
+
+def test_gp_parameter_protocol():
+    bounds_drw = [(4.0, 6.0), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+    assert gpmodel.k == 5
+    assert gpmodel.parameter_names == ("kernel:terms[0]:log_S0", "kernel:terms[0]:log_omega0", "kernel:terms[1]:log_S0",
+                                       "kernel:terms[1]:log_Q", "kernel:terms[1]:log_omega0")
+    assert gpmodel.gp.get_parameter_bounds() == bounds_drw + bounds_lor
+    gpmodel.gp.set_parameter_vector([5.5, 9.0, 11.0, 2.0, -3.0])
+    assert gpmodel.gp.log_prior() == 0.0
+    gpmodel.gp.set_parameter_vector([6.5, 9.0, 11.0, 2.0, -3.0])
+    assert gpmodel.gp.log_prior() == -np.inf
+    with pytest.raises(AttributeError):
+        gpmodel.max_loglikelihood
+    with pytest.raises(AttributeError):
+        gpmodel.mcmc_samples
+    with pytest.raises(RuntimeError):
+        gpmodel.generate_from_posteriors(2)
+    # dict-style bounds and keyword parameters (tutorial_ppp.ipynb cell 7)
+    k = terms.RealTerm(log_a=1.0, log_c=-2.0, bounds=dict(log_a=(-10, 50), log_c=(-10, 10)))
+    assert k.get_parameter_bounds() == [(-10, 50), (-10, 10)]
+    with pytest.raises(ValueError):
+        terms.RealTerm(log_a=100.0, log_c=-2.0, bounds=dict(log_a=(-10, 50), log_c=(-10, 10)))
+    # mean models of GPModelling._build_mean_model
+    lc = GappyLightcurve(np.arange(50.0), np.random.default_rng(0).normal(10, 1, 50), np.ones(50))
+    assert GPModelling(lc, DampedRandomWalk(0.0, 0.0), "constant").k == 3
+    assert GPModelling(lc, DampedRandomWalk(0.0, 0.0), "linear").k == 4
+    assert GPModelling(lc, DampedRandomWalk(0.0, 0.0), "gaussian").k == 6
+    with pytest.raises(ValueError):
+        GPModelling(lc, DampedRandomWalk(0.0, 0.0), "quadratic")
+    bpl = BendingPowerlaw(2.0, 1.0, 0.0)
+    assert bpl.log_prior() == 0.0
+    bpl.set_parameter_vector([1.0, 2.0, 0.0])
+    assert bpl.log_prior() == -np.inf            # log_S0 < log_Q (celerite_models.py:85-90)
+    with pytest.raises(ValueError):              # like celerite, a non-finite prior at construction raises
+        BendingPowerlaw(1.0, 2.0, 0.0)
+
+
+# ---- tests/models_test.py (6 decimals) ----------------------------------------------------------------------
+
+def test_psd_identities():
+    w = np.arange(1, 1000)
+    np.testing.assert_array_almost_equal(psd_models.BendingPowerlaw(S0=10, omega0=5, Q=0.5)(w),
+                                         celerite_models.DampedRandomWalk(log_S0=np.log(10), log_omega0=np.log(5)).get_psd(w))
+    for Q in [10, 1, 1 / np.sqrt(2), 0.1]:
+        np.testing.assert_array_almost_equal(psd_models.SHO(S0=10, omega0=5, Q=Q)(w),
+                                             terms.SHOTerm(log_S0=np.log(10), log_Q=np.log(Q), log_omega0=np.log(5)).get_psd(w))
+    for rho in [1, 10, 20]:
+        np.testing.assert_array_almost_equal(psd_models.Matern32(sigma=10, rho=rho)(w),
+                                             terms.Matern32Term(log_sigma=np.log(10), log_rho=np.log(rho), eps=1e-15).get_psd(w))
+        np.testing.assert_array_almost_equal(psd_models.Matern32(sigma=10, rho=rho)(w), psd_models.Matern(w, 10, rho, 1, 3 / 2))
+        np.testing.assert_array_almost_equal(psd_models.Matern52(sigma=10, rho=rho)(w), psd_models.Matern(w, 10, rho, 1, 5 / 2))
+    for Q in [1, 10, 100]:
+        for S0 in [1, 10, 100]:
+            np.testing.assert_array_almost_equal(psd_models.Lorentzian(S0=S0, omega0=5, Q=Q)(w),
+                                                 celerite_models.Lorentzian(log_S0=np.log(S0), log_Q=np.log(Q), log_omega0=np.log(5)).get_psd(w))
+    s = psd_models.Lorentzian(1, 80, 0.6) + psd_models.BendingPowerlaw(1, 0.3)
+    np.testing.assert_allclose(s(w), psd_models.Lorentzian(1, 80, 0.6)(w) + psd_models.BendingPowerlaw(1, 0.3)(w))
+
+
+# ---- tests/stats_test.py ------------------------------------------------------------------------------------
+
+def test_distribution_factories_and_chi_statistics():
+    for mean, std in [(10.0, 2.0), (0.5, 0.3)]:
+        d = mstats.create_log_normal(mean, std)
+        assert abs(d.mean() - mean) < 1e-9 and abs(d.var() - std ** 2) < 1e-9
+        d = mstats.create_uniform_distribution(mean, std)
+        assert abs(d.mean() - mean) < 1e-12 and abs(d.var() - std ** 2) < 1e-12
+    p = np.array([1.0, 2.0, 3.0]); m = np.array([2.0, 2.0, 2.0])
+    assert mstats.chi_log_likehood(p, m) == pytest.approx(2 * np.sum(np.log(m) + p / m))
+    sig = np.array([0.5, 1.0, 2.0])
+    assert mstats.chi_cov(p, m, np.diag(1 / sig ** 2)) == pytest.approx(mstats.chi_square(p, m, sig))
+    assert mstats.aicc(-10.0, 100, 3) == pytest.approx(2 * 3 + 20 + 2 * 3 * 4 / 96)
+    assert mstats.bic(-10.0, 100, 3) == pytest.approx(20 + 3 * np.log(100))
+    # the Kraft posterior integrates to one (np.math bit-rot of the reference fixed)
+    from scipy import integrate
+    assert integrate.quad(mstats.kraft_pdf(a=0, b=35).pdf, 0, 35, args=(3, 1.5))[0] == pytest.approx(1.0, abs=1e-6)
+
+
+def test_lrt_pvalue_matches_percentileofscore():
+    from scipy.stats import percentileofscore
+    rng = np.random.default_rng(0)
+    T = rng.chisquare(3, 1000)
+    for t_obs in [0.0, 1.0, 7.3, T[17], 50.0]:
+        assert mstats.lrt_pvalue(T, t_obs) == pytest.approx(1 - percentileofscore(T, t_obs) / 100)
+    s = mstats.lrt_summary(T, 9.0)
+    assert s["n"] == 1000 and s["hist"].sum() == 1000 and s["percentiles"][95.0] == pytest.approx(np.percentile(T, 95))
+    assert np.allclose(mstats.lrt_statistic([-10.0, -8.0], [-7.0, -8.0]), [6.0, 0.0])
+
+
+# ---- sampler (host logic; CPU log-probability) ------------------------------------------------------------------
+
+def test_ensemble_sampler_recovers_gaussian():
+    cov = np.array([[1.0, 0.6], [0.6, 2.0]]); icov = np.linalg.inv(cov)
+    logp = lambda p: -0.5 * np.einsum("bi,ij,bj->b", p, icov, p)
+    s = EnsembleSampler(20, 2, logp, vectorize=True, seed=1)
+    p0 = np.random.default_rng(0).normal(size=(20, 2))
+    for _ in s.sample(p0, iterations=3000):
+        pass
+    chain = s.get_chain(discard=500, flat=True)
+    assert np.allclose(np.cov(chain.T), cov, atol=0.25) and np.allclose(chain.mean(axis=0), 0, atol=0.15)
+    tau = s.get_autocorr_time(tol=0)
+    assert tau.shape == (2,) and np.all(tau > 1) and np.all(tau < 200)
+    assert s.get_chain(discard=10, thin=5).shape == ((3000 - 10 - 4 + 4) // 5, 20, 2)
+    assert s.get_log_prob(discard=10, thin=5, flat=True).shape[0] == s.get_chain(discard=10, thin=5, flat=True).shape[0]
+    with pytest.raises(ValueError):
+        EnsembleSampler(3, 2, logp)
+    with pytest.raises(ValueError):          # linearly dependent walkers (percent = 0 spreads cannot be sampled)
+        next(EnsembleSampler(8, 2, logp, vectorize=True).sample(np.zeros((8, 2)), iterations=1))
+
+
+def test_integrated_time_of_ar1():
+    rng = np.random.default_rng(2)
+    rho = 0.9
+    x = np.zeros((20000, 4, 1))
+    for i in range(1, len(x)):
+        x[i] = rho * x[i - 1] + rng.normal(size=(4, 1))
+    tau = integrated_time(x, tol=0)
+    assert abs(tau[0] - (1 + rho) / (1 - rho)) < 3.0

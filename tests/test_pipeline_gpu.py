@@ -1,0 +1,102 @@
+"""GPU: the user-level workflow end to end -- GPModelling.fit / derive_posteriors /
+generate_from_posteriors / standarized_residuals and the batched LRT driver."""
+import warnings
+
+import numpy as np
+import pytest
+
+from mind_the_gaps_b200 import lrt
+from mind_the_gaps_b200.celerite import GP, terms
+from mind_the_gaps_b200.gpmodelling import GPModelling
+from mind_the_gaps_b200.lightcurves import GappyLightcurve
+from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+from oracle import gp as ogp
+
+from helpers import window
+
+pytestmark = pytest.mark.gpu
+DAY = 86400.0
+
+
+def make_lc(N=200, seed=1):
+    """Config C1: 200-point irregular window, DRW truth, Poisson noise."""
+    t, exposures = window(N, seed)
+    mean = 0.5
+    var = (0.1 * mean) ** 2
+    w = 2 * np.pi / (20 * DAY)
+    rng = np.random.default_rng(seed)
+    y = np.empty(N); y[0] = rng.normal(0, np.sqrt(var))
+    for n in range(1, N):
+        rho = np.exp(-w * (t[n] - t[n - 1]))
+        y[n] = rho * y[n - 1] + rng.normal(0, np.sqrt(var * (1 - rho * rho)))
+    rate = mean + y
+    counts = rng.poisson(rate * exposures)
+    return GappyLightcurve(t, counts / exposures, np.sqrt(counts) / exposures, exposures), np.array([np.log(var), np.log(w)])
+
+
+def test_predict_and_standardised_residuals_match_dense_oracle():
+    lc, truth = make_lc(150, 2)
+    kernel = DampedRandomWalk(truth[0], truth[1]) + terms.JitterTerm(np.log(0.01))
+    gpm = GPModelling(lc, kernel)
+    mu, var = gpm.gp.predict(lc.y, return_var=True, return_cov=False)
+    from oracle import terms as oterms
+    spec = [("drw",), ("jitter",)]
+    co = oterms.coefficients(spec, gpm.gp.get_parameter_vector())
+    diag = (lc.dy + 1e-12) ** 2
+    rmu, rvar = ogp.predict_dense(lc.times, lc.y - lc.mean, diag, *co[:6], jitter=co[6])
+    np.testing.assert_allclose(mu, lc.mean + rmu, rtol=1e-9)
+    np.testing.assert_allclose(var, rvar, rtol=1e-7, atol=1e-12)
+    res = gpm.standarized_residuals()
+    np.testing.assert_allclose(res, (lc.y - (lc.mean + rmu)) / np.sqrt(rvar + co[6]), rtol=1e-6)
+
+
+def test_gpmodelling_fit_and_posteriors_c1():
+    """configs[0]: null-model log-likelihood + fit + emcee-style sampling on one 200-point lightcurve."""
+    np.random.seed(3)
+    lc, truth = make_lc(200, 1)
+    bounds = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    gpm = GPModelling(lc, DampedRandomWalk(truth[0], truth[1], bounds=bounds))
+    sol = gpm.fit()
+    assert sol.success and np.all(np.abs(sol.x - truth) < 1.5)
+    ref = ogp.loglike_params([("drw",)], sol.x[None, :], lc.times, lc.y, lc.dy)[0]
+    assert abs(-sol.fun - ref) < 1e-9 * abs(ref)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpm.derive_posteriors(max_steps=1500, convergence_steps=500, walkers=16, cores=1, progress=False)
+    assert gpm.mcmc_samples.shape[1] == 2 and len(gpm.loglikelihoods) == len(gpm.mcmc_samples)
+    assert gpm.max_loglikelihood <= -sol.fun + 1e-6 and gpm.max_loglikelihood > -sol.fun - 3.0
+    assert np.all(np.abs(gpm.median_parameters - sol.x) < 1.0)
+    assert gpm.tau.shape == (2,) and gpm.get_rstat().shape[1] == 2
+    # every stored log-probability is the oracle's log-likelihood at that sample (flat prior inside the box)
+    idx = np.random.default_rng(0).choice(len(gpm.mcmc_samples), 20)
+    ref = ogp.loglike_params([("drw",)], gpm.mcmc_samples[idx], lc.times, lc.y, lc.dy)
+    np.testing.assert_allclose(gpm.loglikelihoods[idx], ref, rtol=1e-10)
+    lcs = gpm.generate_from_posteriors(nsims=5, cpus=2)
+    assert len(lcs) == 5 and all(len(l.y) == lc.n and np.all(l.dy > 0) for l in lcs)
+    assert abs(np.mean([l.mean for l in lcs]) - lc.mean) < 0.1
+
+
+def test_lrt_driver_null_distribution():
+    lc, truth = make_lc(200, 4)
+    b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    null_kernel = DampedRandomWalk(truth[0], truth[1], bounds=b_drw)
+    alt_kernel = Lorentzian(truth[0] - 2, np.log(20.0), np.log(2 * np.pi / (10 * DAY)),
+                            bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
+        DampedRandomWalk(truth[0], truth[1], bounds=b_drw)
+    rng = np.random.default_rng(5)
+    samples = truth[None, :] + rng.normal(0, 0.15, (96, 2))
+    res = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, n_starts_null=2, n_starts_alt=6, seed=11,
+                               return_lightcurves=True)
+    assert res.T.shape == (96,) and np.all(np.isfinite(res.T))
+    assert np.all(res.T > -1e-4)                      # nested start: the alternative never fits worse
+    assert 0.2 < np.median(res.T) < 12.0 and np.percentile(res.T, 95) < 40.0
+    # the recorded likelihoods are the oracle's at the recorded optima, on the simulated data
+    Y, DY = res.lightcurves
+    for i in (0, 17, 95):
+        l0 = ogp.loglike_params([("drw",)], res.params_null[i][None, :], lc.times, Y[i], DY[i])[0]
+        l1 = ogp.loglike_params([("lorentzian",), ("drw",)], res.params_alt[i][None, :], lc.times, Y[i], DY[i])[0]
+        assert abs(l0 - res.loglike_null[i]) < 1e-9 * abs(l0) and abs(l1 - res.loglike_alt[i]) < 1e-9 * abs(l1)
+    assert 0.0 <= res.pvalue(5.0) <= 1.0
+    # same seed -> same simulations and same statistics
+    res2 = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, n_starts_null=2, n_starts_alt=6, seed=11)
+    np.testing.assert_allclose(res2.loglike_null, res.loglike_null, rtol=1e-12)
