@@ -12,6 +12,8 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/mtg_b200.h"
+#define MTG_LOG2E 1.4426950408889634
+#define MTG_LN2 0.6931471805599453
 
 #define MTG_MAXR 4          // real recursion slots
 #define MTG_MAXC 8          // complex (width-2) recursion slots
@@ -76,7 +78,7 @@ __device__ __forceinline__ bool plan_in_prior(const Plan &pl, const double *__re
 // Per-series coefficients in registers.  DUAL: SHO slots may hold two real terms (Q < 1/2).
 template <int JR, int JC, bool DUAL>
 struct Coef {
-    double ar[JR > 0 ? JR : 1], ncr[JR > 0 ? JR : 1];                       // a, -c
+    double ar[JR > 0 ? JR : 1], ncr[JR > 0 ? JR : 1];                       // a, -c log2(e)
     double ac[JC > 0 ? JC : 1], bc[JC > 0 ? JC : 1], ncc[JC > 0 ? JC : 1], dc[JC > 0 ? JC : 1];
     double a2[(DUAL && JC > 0) ? JC : 1], nc2[(DUAL && JC > 0) ? JC : 1];   // second real term of an overdamped SHO
     bool   pair[(DUAL && JC > 0) ? JC : 1];                                 // true: complex pair
@@ -92,7 +94,7 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
         c.ar[j] = exp(plan_param(pl, x, pl.r_ia[j]));
-        c.ncr[j] = -exp(plan_param(pl, x, pl.r_ic[j]));
+        c.ncr[j] = -exp(plan_param(pl, x, pl.r_ic[j])) * MTG_LOG2E;
         a_sum += c.ar[j];
     }
 #pragma unroll
@@ -126,9 +128,9 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
                               d = 0.0;
                           } } break;
         }
-        c.ac[j] = a; c.bc[j] = b; c.ncc[j] = -cc; c.dc[j] = d;
+        c.ac[j] = a; c.bc[j] = b; c.ncc[j] = -cc * MTG_LOG2E; c.dc[j] = d;
         a_sum += a;
-        if (DUAL) { c.pair[j] = pair; c.a2[j] = a2; c.nc2[j] = -c2; a_sum += a2; }
+        if (DUAL) { c.pair[j] = pair; c.a2[j] = a2; c.nc2[j] = -c2 * MTG_LOG2E; a_sum += a2; }
     }
     c.a_sum = a_sum;
 }

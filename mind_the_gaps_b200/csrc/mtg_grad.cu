@@ -52,11 +52,11 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
         add(pl.r_ia[j], (g.ar[j] + g.a_sum) * c.ar[j]);
-        add(pl.r_ic[j], g.cr[j] * (-c.ncr[j]));
+        add(pl.r_ic[j], g.cr[j] * (-c.ncr[j] * MTG_LN2));
     }
 #pragma unroll
     for (int j = 0; j < JC; ++j) {
-        const double a = c.ac[j], b = c.bc[j], cc = -c.ncc[j], d = c.dc[j];
+        const double a = c.ac[j], b = c.bc[j], cc = -c.ncc[j] * MTG_LN2, d = c.dc[j];
         const double ga = g.ac[j] + g.a_sum, gb = g.bc[j], gc = g.cc[j], gd = g.dc[j];
         const int *ix = pl.c_idx[j];
         switch (pl.c_kind[j]) {
@@ -74,7 +74,7 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
                 add(ix[1], ga * a + gb * b * (1.0 - r) - gc * cc + gd * d * (r - 1.0));
                 add(ix[2], ga * a + gb * b + gc * cc + gd * d);
             } else {
-                const double a2 = c.a2[j], c2 = -c.nc2[j];
+                const double a2 = c.a2[j], c2 = -c.nc2[j] * MTG_LN2;
                 const double ga2 = g.a2[j] + g.a_sum, gc2 = g.c2[j];
                 const double f = sqrt(1.0 - 4.0 * Q * Q);
                 const double h = 0.5 * (a + a2);                       // = 1/2 S0 w0 Q
@@ -182,19 +182,19 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
         double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
         double cdv[JC > 0 ? JC : 1], sdv[JC > 0 ? JC : 1];
 #pragma unroll
-        for (int j = 0; j < JR; ++j) { p[j] = exp(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
+        for (int j = 0; j < JR; ++j) { p[j] = mtgm::exp2_nonpos(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
-            const double e = exp(c.ncc[j] * dt);
+            const double e = mtgm::exp2_nonpos(c.ncc[j] * dt);
             if (!DUAL || c.pair[j]) {
-                double sd, cd; sincos(c.dc[j] * tn, &sd, &cd);
+                double sd, cd; mtgm::sincos_fast(c.dc[j] * tn, &sd, &cd);
                 cdv[j] = cd; sdv[j] = sd;
                 p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
                 u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd); u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
                 v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
             } else {
                 cdv[j] = 1.0; sdv[j] = 0.0;
-                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = exp(c.nc2[j] * dt);
+                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = mtgm::exp2_nonpos(c.nc2[j] * dt);
                 u[JR + 2 * j] = c.ac[j]; u[JR + 2 * j + 1] = c.a2[j];
                 v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
             }

@@ -14,12 +14,17 @@
 // next step's values are prefetched one step ahead.
 #include "mtg_recursion.cuh"
 
+#ifndef K1_THREADS
 #define K1_THREADS 128
+#endif
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 1
+#endif
 #define K1_TILE 256
 
 // SHARED: S == 1, rates/variances staged through smem with the times.
 template <int JR, int JC, bool DUAL, bool SHARED>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
 {
     constexpr int NARR = SHARED ? 3 : 1;

@@ -7,6 +7,7 @@
 // mind_the_gaps/gpmodelling.py:54,152,169); restated in SURVEY.md 3.1.
 #pragma once
 #include "mtg_common.cuh"
+#include "mtg_math.cuh"
 
 template <int J> __device__ __forceinline__ constexpr int tri(int j, int k)   // j <= k, upper triangle
 { return j * J - (j * (j - 1)) / 2 + (k - j); }
@@ -37,19 +38,19 @@ struct K1State {
         tp = tn;
         double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
 #pragma unroll
-        for (int j = 0; j < JR; ++j) { p[j] = exp(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
+        for (int j = 0; j < JR; ++j) { p[j] = mtgm::exp2_nonpos(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
-            const double e = exp(c.ncc[j] * dt);
+            const double e = mtgm::exp2_nonpos(c.ncc[j] * dt);
             if (!DUAL || c.pair[j]) {
                 double sd, cd;
-                sincos(c.dc[j] * tn, &sd, &cd);
+                mtgm::sincos_fast(c.dc[j] * tn, &sd, &cd);
                 p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
                 u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd);
                 u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
                 v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
             } else {
-                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = exp(c.nc2[j] * dt);
+                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = mtgm::exp2_nonpos(c.nc2[j] * dt);
                 u[JR + 2 * j] = c.ac[j]; u[JR + 2 * j + 1] = c.a2[j];
                 v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
             }
@@ -84,7 +85,11 @@ struct K1State {
         bad = bad || !(D > 0.0);
         // sum log D as the log of a running product, renormalised every 4 steps
         prod *= D;
-        if ((n & 3) == 3) { int e; prod = frexp(prod, &e); esum += e; }
+        if ((n & 3) == 3) {                      // frexp on a positive normal number, branch free
+            const int hi = __double2hiint(prod);
+            esum += ((hi >> 20) & 0x7ff) - 1022;
+            prod = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(prod));
+        }
         Dp = D; zp = z;
     }
 
