@@ -76,6 +76,9 @@ int mtg_build_plan(const mtg_model_t *m, Plan *pl)
             if (!chk(ix[i])) { mtg_set_error("term %d parameter index %d out of range", k, ix[i]); return MTG_EINVAL; }
     }
     pl->jr = jr; pl->jc = jc; pl->j_celerite = jcel;
+    pl->b_zero = 1;
+    for (int j = 0; j < jc; ++j)
+        if (pl->c_kind[j] != CS_COMPLEX3 && pl->c_kind[j] != CS_LORENTZIAN && pl->c_kind[j] != CS_COSINUS) pl->b_zero = 0;
     if (jr + 2 * jc > MTG_MAX_J) goto toowide;
     pl->mean_kind = m->mean_kind;
     {

@@ -25,6 +25,7 @@ struct Plan {
     int32_t jr, jc;                 // recursion slots actually computed
     int32_t j_celerite;             // width as celerite counts it (incl. degenerate real terms)
     int32_t has_sho;                // any SHO slot (can flip to two real terms when Q < 1/2)
+    int32_t b_zero;                 // every complex slot has b == 0 structurally (ComplexTerm(a,c,d), Lorentzian, Cosinus)
     int32_t r_ia[MTG_MAXR], r_ic[MTG_MAXR];     // real slot: a = exp(p[ia]), c = exp(p[ic])
     int32_t c_kind[MTG_MAXC];
     int32_t c_idx[MTG_MAXC][4];
@@ -83,6 +84,7 @@ struct Coef {
     double a2[(DUAL && JC > 0) ? JC : 1], nc2[(DUAL && JC > 0) ? JC : 1];   // second real term of an overdamped SHO
     bool   pair[(DUAL && JC > 0) ? JC : 1];                                 // true: complex pair
     double a_sum;                                                           // jitter + sum a
+    bool   b_zero;                                                          // warp-uniform: all b == 0
 };
 
 template <int JR, int JC, bool DUAL>
@@ -133,6 +135,7 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
         if (DUAL) { c.pair[j] = pair; c.a2[j] = a2; c.nc2[j] = -c2 * MTG_LOG2E; a_sum += a2; }
     }
     c.a_sum = a_sum;
+    c.b_zero = pl.b_zero != 0;
 }
 
 // mean model value at time tn (gpmodelling.py:62-124; models/mean_models.py:6-31)

@@ -20,6 +20,11 @@
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 1
 #endif
+#ifndef K1_UNROLL
+#define K1_UNROLL 2
+#endif
+#define K1_STR2(x) #x
+#define K1_STR(x) K1_STR2(x)
 #define K1_TILE 256
 
 // SHARED: S == 1, rates/variances staged through smem with the times.
@@ -87,7 +92,7 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
             __syncthreads();
         }
         const double *st_t = &sm[st][0][0];
-#pragma unroll 1
+_Pragma(K1_STR(unroll K1_UNROLL))
         for (int i = 0; i < cnt; ++i) {
             const int n = n0 + i;
             const double tn = st_t[i];

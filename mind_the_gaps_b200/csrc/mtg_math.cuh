@@ -47,7 +47,8 @@ __device__ __forceinline__ double exp2_nonpos(double t)
     for (int i = 10; i >= 0; --i) p = fma(p, r, EXP2_C[i]);
     const int hi = __double2hiint(p) + (k << 20);           // p in [0.70, 1.42]: scale by 2^k in the exponent field
     p = __hiloint2double(hi, __double2loint(p));
-    return t < EXP2_K[1] ? 0.0 : p;
+    // t < -1020 decided on the high word (integer pipe): for t <= 0 a larger unsigned high word means a more negative t
+    return (unsigned)__double2hiint(t) > 0xC08FE000u ? 0.0 : p;
 }
 // exp(x) for x <= 0 through the same kernel (test hook / occasional use)
 __device__ __forceinline__ double exp_nonpos(double x) { return exp2_nonpos(x * MTG_LOG2E); }
@@ -55,7 +56,7 @@ __device__ __forceinline__ double exp_nonpos(double x) { return exp2_nonpos(x * 
 // sin(x), cos(x) for finite x; Cody-Waite three-term reduction below 1e5, libdevice beyond
 __device__ __forceinline__ void sincos_fast(double x, double *sn, double *cs)
 {
-    if (!(fabs(x) < TRIG_K[5])) { sincos(x, sn, cs); return; }
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) { sincos(x, sn, cs); return; }      // |x| >= 1e5 (or NaN/inf): libdevice
     const double kd = fma(x, TRIG_K[0], TRIG_K[4]);
     const int q = __double2loint(kd);
     const double kf = kd - TRIG_K[4];

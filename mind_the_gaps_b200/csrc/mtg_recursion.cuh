@@ -46,8 +46,11 @@ struct K1State {
                 double sd, cd;
                 mtgm::sincos_fast(c.dc[j] * tn, &sd, &cd);
                 p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
-                u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd);
-                u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
+                if (c.b_zero) { u[JR + 2 * j] = c.ac[j] * cd; u[JR + 2 * j + 1] = c.ac[j] * sd; }
+                else {
+                    u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd);
+                    u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
+                }
                 v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
             } else {
                 p[JR + 2 * j] = e; p[JR + 2 * j + 1] = mtgm::exp2_nonpos(c.nc2[j] * dt);
@@ -82,7 +85,7 @@ struct K1State {
 #pragma unroll
         for (int j = 0; j < J; ++j) W[j] = (v[j] - su[j]) * rD;
         chi2 = fma(z * z, rD, chi2);
-        bad = bad || !(D > 0.0);
+        bad = bad || (__double2hiint(D) <= 0);          // D <= 0 (or denormal): not positive definite; NaN surfaces in the final isfinite test
         // sum log D as the log of a running product, renormalised every 4 steps
         prod *= D;
         if ((n & 3) == 3) {                      // frexp on a positive normal number, branch free
