@@ -150,13 +150,71 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank):
+    """K2 (loglike + gradient) throughput, the latency-bound 64-walker call of config C2 as emcee would
+    issue it, and a short LRT (simulate + fit null + fit alternative) -- reported under "extras"."""
+    out = {}
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    # K2: 64 walkers x 1024 ensembles (tape 7.3 GB)
+    Bg = WALKERS * 1024
+    g_ll = torch.empty(Bg, dtype=torch.float64, device=dev); g_g = torch.empty((Bg, 5), dtype=torch.float64, device=dev)
+    g_st = torch.empty(Bg, dtype=torch.int32, device=dev)
+    def k2():
+        _native.check(lib.mtg_loglike_grad_dev(ctypes.byref(model), N_POINTS, 1, Bg, Bg, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(),
+                                               None, d_p.data_ptr(), g_ll.data_ptr(), g_g.data_ptr(), g_st.data_ptr(), 0, stream.cuda_stream))
+    ms = timed(k2, 3)
+    tape_bytes = Bg * N_POINTS * 14 * 8
+    out["loglike_grad"] = {"batch": Bg, "ms": ms, "evals_per_s": Bg / (ms * 1e-3), "tape_GB_written_and_read": 2 * tape_bytes / 1e9,
+                           "tape_GBps": 2 * tape_bytes / (ms * 1e-3) / 1e9}
+    # the 32-parameter-set half-ensemble call of a 64-walker emcee step (latency bound by construction)
+    s_ll = torch.empty(32, dtype=torch.float64, device=dev); s_st = torch.empty(32, dtype=torch.int32, device=dev)
+    def k1_small():
+        _native.check(lib.mtg_loglike_dev(ctypes.byref(model), N_POINTS, 1, 32, 32, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
+                                          d_p.data_ptr(), s_ll.data_ptr(), s_st.data_ptr(), _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
+    ms = timed(k1_small, 20)
+    out["half_ensemble_of_64_walkers"] = {"batch": 32, "ms": ms, "evals_per_s": 32 / (ms * 1e-3)}
+    # a short LRT: DRW null vs Lorentzian + DRW alternative on the same 1000-point window
+    try:
+        from mind_the_gaps_b200 import lrt
+        from mind_the_gaps_b200.lightcurves import GappyLightcurve
+        from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+        from helpers import c2_truth, window
+        tt_, exposures = window(N_POINTS, 2)
+        lc = GappyLightcurve(tt_, np.full(N_POINTS, 0.5), np.full(N_POINTS, 0.02), exposures)
+        tr = c2_truth()
+        b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+        null_k = DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
+        alt_k = Lorentzian(tr[2] - 2, np.log(20.0), tr[4], bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
+            DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
+        n_sims = 512
+        samples = tr[None, :2] + np.random.default_rng(5 + rank).normal(0, 0.1, (n_sims, 2))
+        t0 = time.perf_counter()
+        res = lrt.simulate_and_fit(lc, null_k, alt_k, samples, n_starts_null=2, n_starts_alt=8, seed=3, distributed=False)
+        wall = time.perf_counter() - t0
+        out["lrt"] = {"sims": n_sims, "wall_s": wall, "sims_per_s": n_sims / wall, "n_fft": int(lc.get_simulator(null_k.get_psd).fftndatapoints),
+                      "starts": {"null": 2, "alt": 8}, "timings_ms": res.timings, "T_median": float(np.median(res.T)),
+                      "T_p95": float(np.percentile(res.T, 95)), "all_finite": bool(np.all(np.isfinite(res.T)))}
+    except Exception as exc:          # secondary: never fail the headline line
+        out["lrt"] = {"error": repr(exc)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ensembles", type=int, default=4736, help="64-walker ensembles per GPU (4736 = 148 SMs x 32)")
+    ap.add_argument("--ensembles", type=int, default=5920,
+                    help="64-walker ensembles per GPU (5920 x 64 = 148 SMs x 512 resident threads x 5 full waves)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (gradient, small batch, LRT)")
     ap.add_argument("--ref-sample", type=int, default=65536, help="parameter sets per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -247,6 +305,11 @@ def main():
     h2d = B * 5 * 8 + 3 * N_POINTS * 8
     d2h = B * 8 + B * 4
 
+    # ---- secondary measurements (outside the timed region of the headline metric) ----------------
+    extras = {}
+    if not args.no_extras:
+        extras = secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank)
+
     tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -289,6 +352,8 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "wall_s_timed_region": wall,
         }
+        if not args.no_extras:
+            line["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
             rate, n, dt, cores = cpu_port_rate(B, seconds=10.0)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",

@@ -22,7 +22,7 @@ from . import _native
 from .celerite import GP
 from .stats import lrt_pvalue, lrt_statistic
 
-__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts"]
+__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts", "all_gather_rows"]
 
 
 class LRTResult(object):
@@ -41,6 +41,27 @@ def shard_range(n, rank, world):
     base, rem = divmod(int(n), int(world))
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(dist, local_rows, n_total, device=None):
+    """Gather the per-rank row blocks of a ``shard_range`` partition into the full ``(n_total, width)``
+    array on every rank (one NCCL / gloo all-gather of equal-sized, NaN-padded blocks)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    counts = [shard_range(n_total, r, world) for r in range(world)]
+    nmax = max(b - a for a, b in counts)
+    local_rows = np.atleast_2d(np.asarray(local_rows, dtype=np.float64))
+    width = local_rows.shape[1]
+    if local_rows.shape[0] != counts[rank][1] - counts[rank][0]:
+        raise ValueError("rank %d holds %d rows, its shard has %d" % (rank, local_rows.shape[0], counts[rank][1] - counts[rank][0]))
+    pad = np.full((nmax, width), np.nan)
+    pad[:local_rows.shape[0]] = local_rows
+    send = torch.from_numpy(pad)
+    if device is not None:
+        send = send.to(device)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send)
+    return np.concatenate([recv[r].cpu().numpy()[: counts[r][1] - counts[r][0]] for r in range(world)], axis=0)
 
 
 def _bounds_arrays(gp):
@@ -187,17 +208,10 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     timings = {"simulate_ms": t_sim, "fit_null_ms": t_null, "fit_alt_ms": t_alt, "n_local": L}
 
     if dist is not None and world > 1:
-        counts = [shard_range(n_total, r, world) for r in range(world)]
-        nmax = max(b - a for a, b in counts)
-        width = 5 + nd0 + nd1
-        pack = np.full((nmax, width), np.nan)
-        pack[:L, 0] = out_T; pack[:L, 1] = out_l0; pack[:L, 2] = out_l1; pack[:L, 3] = out_s0; pack[:L, 4] = out_s1
-        pack[:L, 5:5 + nd0] = out_p0; pack[:L, 5 + nd0:] = out_p1
-        send = torch.from_numpy(pack).to(device)
-        recv = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(recv, send)
-        parts = [recv[r].cpu().numpy()[: counts[r][1] - counts[r][0]] for r in range(world)]
-        allp = np.concatenate(parts, axis=0)
+        pack = np.empty((L, 5 + nd0 + nd1))
+        pack[:, 0] = out_T; pack[:, 1] = out_l0; pack[:, 2] = out_l1; pack[:, 3] = out_s0; pack[:, 4] = out_s1
+        pack[:, 5:5 + nd0] = out_p0; pack[:, 5 + nd0:] = out_p1
+        allp = all_gather_rows(dist, pack, n_total, device)
         res = LRTResult(allp[:, 0], allp[:, 1], allp[:, 2], allp[:, 5:5 + nd0], allp[:, 5 + nd0:],
                         allp[:, 3].astype(np.int32), allp[:, 4].astype(np.int32), timings)
     else:
