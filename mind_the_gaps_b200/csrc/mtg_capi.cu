@@ -34,6 +34,24 @@ extern "C" int mtg_device_count(void)
 }
 extern "C" int mtg_set_device(int device) { return mtg_cuda_check(cudaSetDevice(device), "cudaSetDevice"); }
 
+// Stream-ordered scratch (K2 tape, L-BFGS state) comes from the device's default memory pool; keep
+// freed blocks cached in the pool instead of returning them to the driver at every synchronisation,
+// otherwise each call pays a multi-GB cudaMalloc.
+int mtg_pool_setup()
+{
+    static std::mutex mu; static bool done[64] = {false};
+    int dev = 0;
+    MTG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    cudaMemPool_t pool;
+    MTG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    MTG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return 0;
+}
+
 // ---- model -> plan ------------------------------------------------------------------------------
 int mtg_build_plan(const mtg_model_t *m, Plan *pl)
 {

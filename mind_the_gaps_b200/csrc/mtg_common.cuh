@@ -193,6 +193,7 @@ size_t mtg_k2_tape_bytes_per_series(const Plan &pl, int N);
 int    mtg_k2_chunk(const Plan &pl, int N, int B);
 // a.B work items (series a.index[i] when a.index != NULL, limited to *a.count when a.count != NULL)
 int    mtg_k2_run(const Plan &pl, const BatchArgs &a, double *tape, int chunk, cudaStream_t stream);
+int  mtg_pool_setup();
 void mtg_set_error(const char *fmt, ...);
 int  mtg_cuda_check(cudaError_t e, const char *what);
 void mtg_count_launch(uint64_t n = 1);

@@ -386,6 +386,7 @@ extern "C" int mtg_loglike_grad_dev(const mtg_model_t *model, int N, int S, int 
     Plan pl;
     int rc = mtg_build_plan(model, &pl);
     if (rc) return rc;
+    if ((rc = mtg_pool_setup())) return rc;
     const int chunk = mtg_k2_chunk(pl, N, B);
     double *tape = nullptr;
     MTG_CUDA(cudaMallocAsync((void **)&tape, mtg_k2_tape_bytes_per_series(pl, N) * (size_t)chunk, stream));

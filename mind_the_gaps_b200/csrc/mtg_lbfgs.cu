@@ -246,6 +246,7 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     cub::CountingInputIterator<int32_t> iota(0);
     cub::DeviceSelect::Flagged((void *)nullptr, cub_bytes, iota, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, B, stream);
     const size_t total = n_dbl * 8 + n_int * 4 + cub_bytes + 1024;
+    if ((rc = mtg_pool_setup())) return rc;
     char *base = nullptr;
     MTG_CUDA(cudaMallocAsync((void **)&base, total, stream));
     double *dptr = (double *)base;

@@ -96,7 +96,8 @@ def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
 
 def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
                      extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
-                     max_iter=200, device=None, distributed=None, chunk=4096, return_lightcurves=False):
+                     max_iter=200, device=None, distributed=None, chunk=4096, return_lightcurves=False,
+                     simulator_kwargs=None):
     """Simulate one lightcurve per row of ``null_samples`` (posterior draws of the null kernel's
     parameters) on the window of ``lightcurve`` and MLE-fit each with both kernels.
 
@@ -139,7 +140,8 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         null_slots = list(range(nd1 - nd0, nd1)) if tail == [strip(s) for s in n0] and head != tail else list(range(nd0))
     x_alt0 = gp1.get_parameter_vector().copy()
 
-    sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor)
+    sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor,
+                                   **(simulator_kwargs or {}))
     h = sim._sim()
     N = lightcurve.n
     t_dev = torch.from_numpy(np.ascontiguousarray(lightcurve.times, dtype=np.float64)).to(device)

@@ -83,6 +83,26 @@ class E13Simulator(BaseSimulatorMethod):
         return self.adjust_lightcurve_pdf(segment, self.pdfmethod(self.meanrate, sample_std), max_iter=self.max_iter)
 
 
+def _next_smooth(n):
+    """Smallest 7-smooth integer (2^a 3^b 5^c 7^d) that is >= n."""
+    best = None
+    p7 = 1
+    while p7 < 2 * n:
+        p5 = p7
+        while p5 < 2 * n:
+            p3 = p5
+            while p3 < 2 * n:
+                v = p3
+                while v < n:
+                    v *= 2
+                if best is None or v < best:
+                    best = v
+                p3 *= 3
+            p5 *= 5
+        p7 *= 7
+    return int(best)
+
+
 _PDF = {"gaussian": _native.PDF_GAUSSIAN, "lognormal": _native.PDF_LOGNORMAL, "uniform": _native.PDF_UNIFORM}
 
 
@@ -91,7 +111,7 @@ class Simulator(object):
 
     def __init__(self, psd_model, times, exposures, mean, pdf="gaussian", bkg_rate=None, bkg_rate_err=None,
                  sigma_noise=None, aliasing_factor=2, extension_factor=10, epsilon=1.001, max_iter=400,
-                 random_state=None):
+                 random_state=None, fft_length="exact"):
         if extension_factor < 1:
             raise ValueError("Extension factor must be greater than 1")
         if epsilon < 1:
@@ -119,6 +139,13 @@ class Simulator(object):
         self.sim_duration = end_time - start_time
         duration = (times[-1] - times[0]) * extension_factor
         self.sim_timestamps = np.arange(start_time - self.sim_dt, start_time + duration + self.sim_dt, self.sim_dt)
+        if fft_length == "fast":
+            # NOT the reference's behaviour (opt-in): lengthen the regular grid to the next 7-smooth length so
+            # the FFT avoids Bluestein's algorithm; a real window easily gives a prime length
+            n = _next_smooth(len(self.sim_timestamps))
+            self.sim_timestamps = (start_time - self.sim_dt) + np.arange(n) * self.sim_dt
+        elif fft_length != "exact":
+            raise ValueError("fft_length must be 'exact' or 'fast'")
         self.fftndatapoints = len(self.sim_timestamps)
         self.pdf = pdf
         self.max_iter = max_iter
