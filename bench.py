@@ -193,7 +193,7 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
         null_k = DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
         alt_k = Lorentzian(tr[2] - 2, np.log(20.0), tr[4], bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
             DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
-        n_sims = 512
+        n_sims = 2048
         samples = tr[None, :2] + np.random.default_rng(5 + rank).normal(0, 0.1, (n_sims, 2))
         runs = {}
         for mode in ("exact", "fast"):
@@ -202,7 +202,7 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
                                        simulator_kwargs={"fft_length": mode})
             wall = time.perf_counter() - t0
             runs[mode] = {"wall_s": wall, "sims_per_s": n_sims / wall, "timings_ms": res.timings,
-                          "n_fft": int(lc.get_simulator(null_k.get_psd, fft_length=mode).fftndatapoints)}
+                          "n_fft": int(lc.get_simulator(null_k.get_psd, extension_factor=2, fft_length=mode).fftndatapoints)}
         out["lrt"] = {"sims": n_sims, "fft_length": runs, "note": "exact = the reference's grid length (prime here -> Bluestein FFT); fast = opt-in 7-smooth length",
                       "wall_s": wall, "sims_per_s": n_sims / wall,
                       "starts": {"null": 2, "alt": 8}, "timings_ms": res.timings, "T_median": float(np.median(res.T)),
@@ -348,7 +348,9 @@ def main():
                     "api": "GP.log_likelihood_batch -> mtg_loglike_host (pinned host buffers)"},
             "gpu_launches": kernel_launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk.value, "unit": "TFLOP/s",
-                         "frac": achieved_tf / pk.value if pk.value else None, "traffic": None,
+                         "frac": achieved_tf / pk.value if pk.value else None,
+                         "traffic": 15241728 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
+                         "traffic_source": "profiles/r01c_k1_loglike_ncu_full_raw.csv (ncu --set full, 378880 series), scaled to this batch",
                          "kernel": "k1_loglike<1,1,false,true>",
                          "flops_per_eval": FLOPS_PER_EVAL, "flops_per_eval_computed_J3": FLOPS_PER_EVAL_COMPUTE,
                          "peak_source": "mtg_fp64_peak_probe: DFMA microbenchmark measured in this run "
