@@ -262,8 +262,10 @@ int mtg_host_free(void *ptr);
 int mtg_fp64_peak_probe(double *out_tflops, double *out_ms);
 /* Writes `bytes` of device memory (L2 flush between timed iterations). */
 int mtg_l2_flush(void *scratch_dev, uint64_t bytes, void *stream);
-/* Test hook: the inner loop's own 2^x (x <= 0) and sincos evaluated on x[n]. */
-int mtg_test_math_host(int n, const double *x, double *out_exp, double *out_sin, double *out_cos);
+/* Test hook: the inner loop's own 2^x (x <= 0), sincos and 1/|x| evaluated on x[n].
+ * variant 0 = polynomial kernels, 1 = the table-driven kernels K1/K2 run (csrc/mtg_math.cuh). */
+int mtg_test_math_host(int n, int variant, const double *x, double *out_exp, double *out_sin, double *out_cos,
+                       double *out_rcp);
 /* number of kernel launches issued by this library since load (bench.py gpu_launches claim) */
 uint64_t mtg_launch_count(void);
 

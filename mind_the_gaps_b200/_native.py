@@ -108,7 +108,7 @@ SIGNATURES = {
     "mtg_predict_host": (ctypes.c_int, [_mp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mtg_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "mtg_host_free": (ctypes.c_int, [_vp]),
-    "mtg_test_math_host": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "mtg_test_math_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mtg_fp64_peak_probe": (ctypes.c_int, [_dp, _dp]),
     "mtg_l2_flush": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp]),
     "mtg_launch_count": (ctypes.c_uint64, []),

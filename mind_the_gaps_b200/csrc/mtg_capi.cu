@@ -356,26 +356,34 @@ extern "C" int mtg_l2_flush(void *scratch_dev, uint64_t bytes, void *stream)
 
 // ---- test hook for the device math of the inner loop (tests/test_math_gpu.py) --------------------------
 #include "mtg_math.cuh"
-__global__ void k_test_math(int n, const double *__restrict__ x, double *__restrict__ e, double *__restrict__ s, double *__restrict__ c)
+__global__ void k_test_math(int n, int variant, const double *__restrict__ x, double *__restrict__ e, double *__restrict__ s,
+                            double *__restrict__ c, double *__restrict__ rc)
 {
+    __shared__ alignas(16) double tabs_sm[MTG_TABS_DOUBLES];
+    const mtgm::Tabs tb = mtgm::tabs_fill(tabs_sm);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    e[i] = mtgm::exp2_nonpos(x[i]);
     double sn, cs;
-    mtgm::sincos_fast(x[i], &sn, &cs);
+    if (variant == 0) { e[i] = mtgm::exp2_nonpos(x[i]); mtgm::sincos_fast(x[i], &sn, &cs); }
+    else { e[i] = mtgm::exp2_nonpos_tab(x[i], tb); mtgm::sincos_tab(x[i], tb, &sn, &cs); }
     s[i] = sn; c[i] = cs;
+    rc[i] = mtgm::rcp_pos(fabs(x[i]));
 }
-extern "C" int mtg_test_math_host(int n, const double *x, double *out_exp, double *out_sin, double *out_cos)
+extern "C" int mtg_test_math_host(int n, int variant, const double *x, double *out_exp, double *out_sin, double *out_cos,
+                                  double *out_rcp)
 {
-    if (n < 1 || !x || !out_exp || !out_sin || !out_cos) { mtg_set_error("mtg_test_math_host: bad argument"); return MTG_EINVAL; }
+    if (n < 1 || !x || !out_exp || !out_sin || !out_cos || !out_rcp) { mtg_set_error("mtg_test_math_host: bad argument"); return MTG_EINVAL; }
     double *d = nullptr;
-    MTG_CUDA(cudaMalloc((void **)&d, sizeof(double) * 4 * (size_t)n));
-    MTG_CUDA(cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice));
-    k_test_math<<<(n + 255) / 256, 256>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+    const size_t m = (size_t)n;
+    MTG_CUDA(cudaMalloc((void **)&d, sizeof(double) * 5 * m));
+    MTG_CUDA(cudaMemcpy(d, x, sizeof(double) * m, cudaMemcpyHostToDevice));
+    k_test_math<<<(n + 255) / 256, 256>>>(n, variant, d, d + m, d + 2 * m, d + 3 * m, d + 4 * m);
     mtg_count_launch();
-    int rc = mtg_cuda_check(cudaMemcpy(out_exp, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost), "d2h");
-    if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_sin, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost), "d2h");
-    if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_cos, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost), "d2h");
+    int rc = mtg_cuda_check(cudaMemcpy(out_exp, d + m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");
+    if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_sin, d + 2 * m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");
+    if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_cos, d + 3 * m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");
+    if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_rcp, d + 4 * m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");
     cudaFree(d);
     return rc;
 }

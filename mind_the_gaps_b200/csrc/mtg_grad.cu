@@ -96,6 +96,9 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
     constexpr int J = JR + 2 * JC;
     constexpr int NS = J * (J + 1) / 2;
     constexpr int K = NS + 2 * J + 2;                       // tape doubles per step: S, f, W, D, z
+    __shared__ alignas(16) double tabs_sm[MTG_TABS_DOUBLES];
+    const mtgm::Tabs tb = mtgm::tabs_fill(tabs_sm);
+    __syncthreads();
     const int lb = blockIdx.x * K2_THREADS + threadIdx.x;   // index inside the chunk
     if (lb >= Bc) return;
     if (a.count && b0 + lb >= *a.count) return;
@@ -122,12 +125,12 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
     for (int n = 0; n < N; ++n) {
         const double tn = t_nx, yn = y_nx, dn = d_nx;
         if (n + 1 < N) { t_nx = __ldg(a.t + n + 1); y_nx = __ldg(yp + (size_t)(n + 1) * S); d_nx = __ldg(dp + (size_t)(n + 1) * S); }
-        s.step(c, tn, yn - mean(tn), dn, n);
+        s.step(c, tb, tn, yn - mean(tn), dn, n);
         double *rec = tp + (size_t)n * K * Bs;
 #pragma unroll
         for (int i = 0; i < NS; ++i) __stcs(rec + (size_t)i * Bs, s.S[i]);
 #pragma unroll
-        for (int j = 0; j < J; ++j) { __stcs(rec + (size_t)(NS + j) * Bs, s.f[j]); __stcs(rec + (size_t)(NS + J + j) * Bs, s.W[j]); }
+        for (int j = 0; j < J; ++j) { __stcs(rec + (size_t)(NS + j) * Bs, s.f[j]); __stcs(rec + (size_t)(NS + J + j) * Bs, s.W[j] * s.rDp); }
         __stcs(rec + (size_t)(NS + 2 * J) * Bs, s.Dp);
         __stcs(rec + (size_t)(NS + 2 * J + 1) * Bs, s.zp);
     }
@@ -182,24 +185,24 @@ k2_loglike_grad(const __grid_constant__ Plan pl, const BatchArgs a, double *__re
         double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
         double cdv[JC > 0 ? JC : 1], sdv[JC > 0 ? JC : 1];
 #pragma unroll
-        for (int j = 0; j < JR; ++j) { p[j] = mtgm::exp2_nonpos(c.ncr[j] * dt); u[j] = c.ar[j]; v[j] = 1.0; }
+        for (int j = 0; j < JR; ++j) { p[j] = mtgm::exp2_nonpos_tab(c.ncr[j] * dt, tb); u[j] = c.ar[j]; v[j] = 1.0; }
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
-            const double e = mtgm::exp2_nonpos(c.ncc[j] * dt);
+            const double e = mtgm::exp2_nonpos_tab(c.ncc[j] * dt, tb);
             if (!DUAL || c.pair[j]) {
-                double sd, cd; mtgm::sincos_fast(c.dc[j] * tn, &sd, &cd);
+                double sd, cd; mtgm::sincos_tab(c.dc[j] * tn, tb, &sd, &cd);
                 cdv[j] = cd; sdv[j] = sd;
                 p[JR + 2 * j] = e; p[JR + 2 * j + 1] = e;
                 u[JR + 2 * j] = fma(c.ac[j], cd, c.bc[j] * sd); u[JR + 2 * j + 1] = fma(c.ac[j], sd, -c.bc[j] * cd);
                 v[JR + 2 * j] = cd; v[JR + 2 * j + 1] = sd;
             } else {
                 cdv[j] = 1.0; sdv[j] = 0.0;
-                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = mtgm::exp2_nonpos(c.nc2[j] * dt);
+                p[JR + 2 * j] = e; p[JR + 2 * j + 1] = mtgm::exp2_nonpos_tab(c.nc2[j] * dt, tb);
                 u[JR + 2 * j] = c.ac[j]; u[JR + 2 * j + 1] = c.a2[j];
                 v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
             }
         }
-        const double rD = 1.0 / cD;
+        const double rD = mtgm::rcp_pos(cD);
         // local likelihood terms
         bz = fma(-cz, rD, bz);
         double bWW = 0.0;

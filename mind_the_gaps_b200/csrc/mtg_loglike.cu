@@ -35,6 +35,8 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
     constexpr int NARR = SHARED ? 3 : 1;
     __shared__ alignas(128) double sm[2][NARR][K1_TILE];
     __shared__ alignas(8) uint64_t bar[2];
+    __shared__ alignas(16) double tabs_sm[MTG_TABS_DOUBLES];
+    const mtgm::Tabs tb = mtgm::tabs_fill(tabs_sm);       // visible after the __syncthreads below
 
     const int tid = threadIdx.x;
     const int b_raw = blockIdx.x * K1_THREADS + tid;
@@ -102,7 +104,7 @@ _Pragma(K1_STR(unroll K1_UNROLL))
                 yn = y_nx; dn = d_nx;
                 if (n + 1 < N) { y_nx = __ldg(yp + (size_t)(n + 1) * S); d_nx = __ldg(dp + (size_t)(n + 1) * S); }
             }
-            s.step(c, tn, yn - mean(tn), dn, n);
+            s.step(c, tb, tn, yn - mean(tn), dn, n);
         }
         __syncthreads();                       // every thread is done with stage st
         if (tid == 0 && k + 2 < ntiles && use_bulk(k + 2)) { fence_proxy_async(); issue(k + 2); }

@@ -10,6 +10,7 @@
 // (tests/test_math_gpu.py).
 #pragma once
 #include <cuda_runtime.h>
+#include "mtg_tables.cuh"
 
 namespace mtgm {
 
@@ -71,6 +72,74 @@ __device__ __forceinline__ void sincos_fast(double x, double *sn, double *cs)
     const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
     *sn = (q & 2) ? -a : a;
     *cs = ((q + 1) & 2) ? -b : b;
+}
+
+
+// ---- table-driven variants (the K1/K2 inner loop) ------------------------------------------------
+// The polynomial versions above cost 15 (2^x) and ~21 (sincos) FP64-pipe instructions; K1 is bound by
+// that pipe (profiles/r01c_*), so the inner loop trades FP64 work for one shared-memory lookup each:
+//   2^t   = 2^k * T[j] * 2^r,  t = k + j/256 + r, |r| <= 1/512  -> degree-4 polynomial, 9 FP64 ops
+//   cis x = cis(q pi/128) * cis(r), |r| <= pi/256                 -> sin: 2 terms, cos-1: 3 terms, 15 FP64 ops
+// Tables are correctly rounded (tools/gen_tables.py) and copied global -> shared once per CTA.
+static __constant__ double EXP2T_C[6] = {256.0, -1.0 / 256.0, MTG_EXP2_P1, MTG_EXP2_P2, MTG_EXP2_P3, MTG_EXP2_P4};
+// [0] 128/pi [1] -pi/128 hi [2] -pi/128 lo [3] -1/6 [4] 1/120 [5] -1/2 [6] 1/24 [7] -1/720
+static __constant__ double TRIGT_C[8] = {MTG_TRIG_INV_STEP, -MTG_TRIG_STEP_HI, -MTG_TRIG_STEP_LO,
+                                         -1.0 / 6.0, 1.0 / 120.0, -0.5, 1.0 / 24.0, -1.0 / 720.0};
+
+#define MTG_TABS_DOUBLES (MTG_EXP2_TAB_N + 2 * MTG_TRIG_TAB_N)
+struct Tabs { const double *e2; const double *trig; };      // shared-memory copies
+
+// every thread of the CTA calls this; the caller synchronises before the first lookup
+__device__ __forceinline__ Tabs tabs_fill(double *smem /* MTG_TABS_DOUBLES, 16-byte aligned */)
+{
+    for (int i = threadIdx.x; i < MTG_EXP2_TAB_N; i += blockDim.x) smem[i] = EXP2_TAB[i];
+    for (int i = threadIdx.x; i < 2 * MTG_TRIG_TAB_N; i += blockDim.x) smem[MTG_EXP2_TAB_N + i] = TRIG_TAB[i];
+    Tabs t; t.e2 = smem; t.trig = smem + MTG_EXP2_TAB_N;
+    return t;
+}
+
+// 2^t for t <= 0 (flushes to 0 below 2^-1020), <= 1.1 ulp
+__device__ __forceinline__ double exp2_nonpos_tab(double t, const Tabs &tb)
+{
+    const double kd = fma(t, EXP2T_C[0], EXP2_K[0]);        // round(256 t) in the low mantissa bits
+    const int ki = __double2loint(kd);
+    const double r = fma(kd - EXP2_K[0], EXP2T_C[1], t);    // exact, |r| <= 1/512
+    const double T = tb.e2[ki & (MTG_EXP2_TAB_N - 1)];
+    double q = fma(r, EXP2T_C[5], EXP2T_C[4]);
+    q = fma(q, r, EXP2T_C[3]);
+    q = fma(q, r, EXP2T_C[2]);
+    double p = fma(T, q * r, T);                            // in [0.998, 2.003)
+    const int hi = __double2hiint(p) + ((ki >> 8) << 20);
+    p = __hiloint2double(hi, __double2loint(p));
+    return (unsigned)__double2hiint(t) > 0xC08FE000u ? 0.0 : p;
+}
+
+// sin(x), cos(x) for finite x, absolute error < 2e-16; libdevice beyond |x| = 1e5
+__device__ __forceinline__ void sincos_tab(double x, const Tabs &tb, double *sn, double *cs)
+{
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) { sincos(x, sn, cs); return; }
+    const double kd = fma(x, TRIGT_C[0], TRIG_K[4]);
+    const int q = __double2loint(kd) & (MTG_TRIG_TAB_N - 1);
+    const double kf = kd - TRIG_K[4];
+    double r = fma(kf, TRIGT_C[1], x);
+    r = fma(kf, TRIGT_C[2], r);                             // |r| <= pi/256
+    const double2 CS = *reinterpret_cast<const double2 *>(tb.trig + 2 * q);
+    const double z = r * r;
+    const double sr = fma(r * z, fma(z, TRIGT_C[4], TRIGT_C[3]), r);                   // sin r
+    const double cm = z * fma(z, fma(z, TRIGT_C[7], TRIGT_C[6]), TRIGT_C[5]);          // cos r - 1
+    *sn = fma(CS.y, cm, fma(CS.x, sr, CS.y));
+    *cs = fma(CS.x, cm, fma(-CS.y, sr, CS.x));
+}
+
+// 1/x for a positive normal x: MUFU.RCP64H seed (>= 19 bits) + one cubic Newton step, ~1 ulp.
+// IEEE division costs three more FP64 instructions and a slow-path branch; D <= 0 / denormal / NaN
+// are flagged by the caller independently of this value.
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 
 }  // namespace mtgm
