@@ -105,9 +105,17 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_port_rate(n_sets_hint, seconds=10.0, nthreads=0):
     """Evaluations/s of the oracle's C restatement of celerite on the host cores."""
     from oracle import cref
+    nthreads = nthreads or host_cores()
     spec = [("drw",), ("lorentzian",)]
     t, y, dy, p, _ = workload(4096, 99)
     cref.loglike_params(spec, p[:256], t, y, dy, nthreads=nthreads)          # load + warm
@@ -116,7 +124,7 @@ def cpu_port_rate(n_sets_hint, seconds=10.0, nthreads=0):
     n = int(min(max(rate * seconds, 4096), n_sets_hint))
     t, y, dy, p, _ = workload(n, 98)
     t0 = time.perf_counter(); cref.loglike_params(spec, p, t, y, dy, nthreads=nthreads); dt = time.perf_counter() - t0
-    return n / dt, n, dt, cref.max_threads()
+    return n / dt, n, dt, nthreads
 
 
 def run_reference(args, rank, world):
@@ -127,14 +135,14 @@ def run_reference(args, rank, world):
     spec = [("drw",), ("lorentzian",)]
     n = args.ref_sample
     t, y, dy, p, _ = workload(n, 7)
+    cores = host_cores()          # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(args.warmup):
-        cref.loglike_params(spec, p[:max(256, n // 8)], t, y, dy)
+        cref.loglike_params(spec, p[:max(256, n // 8)], t, y, dy, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cref.loglike_params(spec, p, t, y, dy)
+        cref.loglike_params(spec, p, t, y, dy, nthreads=cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    cores = cref.max_threads()
     line = {
         "impl": "reference", "metric": "celerite loglike evals/s (N=1k, J=4)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,

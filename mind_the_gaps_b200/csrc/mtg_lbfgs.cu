@@ -14,15 +14,22 @@
 // Differences from scipy's L-BFGS-B (Byrd-Lu-Nocedal-Zhu): the generalised-Cauchy-point /
 // subspace-minimisation step is replaced by a projected L-BFGS direction (variables at a bound with
 // the gradient pointing outwards are frozen for the iteration) and the More-Thuente line search by
-// Armijo backtracking with quadratic interpolation and cautious (s.y > 0) updates.  Stopping tests
+// Armijo backtracking with quadratic interpolation, an EXPANSION phase (the step is tripled while the
+// Armijo point still violates the weak-Wolfe curvature condition, slope_t < 0.9 slope_0: without it the
+// rare starts on a likelihood plateau crawl with steps of the size of their gradient for hundreds of
+// iterations, and every straggler costs the whole batch one latency-bound round) and cautious (s.y > 0) updates.  Stopping tests
 // are scipy's: projected-gradient inf-norm <= gtol, relative decrease <= ftol.  Gradients are
 // analytic (K2) instead of 2-point finite differences.
 #include "mtg_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #define LB_THREADS 128
 #define LB_MAXM 10
+#define LB_EXPAND 3.0          // step-length growth factor of the expansion phase
+#define LB_MAX_EXPAND 8       // at most 3^8 times the initial step
 
 struct LbfgsState {
     int B, nd, m;
@@ -31,6 +38,8 @@ struct LbfgsState {
     double *RHO;                  // [m][B]
     double *F, *alpha, *gd;       // [B]
     int32_t *hist_n, *hist_head, *ls_count, *iter, *phase, *status, *restarted;   // [B]
+    double *XC, *GC, *FC;         // [nd][B], [nd][B], [B]  best Armijo point of the current line search (expansion phase)
+    int32_t *has_cand, *n_exp;    // [B]
     double *XT, *LL, *GT;         // [B][nd], [B], [B][nd]   K2 input / outputs
     int32_t *k2_status;           // [B]
     int32_t *flags;               // [B] 1 = still active
@@ -50,6 +59,7 @@ __global__ void k_lbfgs_init(LbfgsState s, LbfgsParams p, const double *__restri
     for (int k = 0; k < p.nd; ++k) s.XT[(size_t)b * p.nd + k] = clampd(x0[(size_t)b * p.nd + k], p.lo[k], p.hi[k]);
     s.phase[b] = 0; s.status[b] = 1; s.iter[b] = 0; s.hist_n[b] = 0; s.hist_head[b] = 0; s.ls_count[b] = 0;
     s.restarted[b] = 0; s.flags[b] = 1; s.F[b] = INFINITY; s.alpha[b] = 1.0; s.gd[b] = 0.0;
+    s.has_cand[b] = 0; s.n_exp[b] = 0;
     list[b] = b;
 }
 
@@ -144,15 +154,34 @@ __global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__res
         }
     } else {
         const double F = s.F[b];
-        double gdx = 0.0, ss = 0.0, yy = 0.0, sy = 0.0;
-        double dx[MTG_MAX_PARAMS], dg[MTG_MAX_PARAMS];
-        for (int k = 0; k < nd; ++k) {
-            const double gk = s.G[(size_t)k * B + b];
-            dx[k] = xt[k] - s.X[(size_t)k * B + b]; dg[k] = gt[k] - gk;
-            gdx += gk * dx[k]; ss += dx[k] * dx[k]; yy += dg[k] * dg[k]; sy += dx[k] * dg[k];
-        }
-        if (isfinite(ft) && ft <= F + 1e-4 * gdx) {
-            // accept the step
+        const bool armijo_at = [&]() {
+            double gdx = 0.0;
+            for (int k = 0; k < nd; ++k) gdx += s.G[(size_t)k * B + b] * (xt[k] - s.X[(size_t)k * B + b]);
+            return isfinite(ft) && ft <= F + 1e-4 * gdx;
+        }();
+        // expansion test (weak Wolfe curvature condition): the slope along the direction at the trial point is still
+        // nearly as steep as at the base point -> the step was too short (plateaus, negative curvature).  Only for
+        // trial points that were not clipped by the box.
+        auto wants_expansion = [&]() {
+            if (s.n_exp[b] >= LB_MAX_EXPAND) return false;
+            const double a0 = s.alpha[b];
+            double slope = 0.0, dmax = 0.0;
+            for (int k = 0; k < nd; ++k) {
+                const double dk = s.Dir[(size_t)k * B + b];
+                if (dk != 0.0 && (xt[k] <= p.lo[k] || xt[k] >= p.hi[k])) return false;
+                slope += gt[k] * dk; dmax = fmax(dmax, fabs(dk));
+            }
+            if (!(slope < 0.9 * s.gd[b])) return false;
+            return LB_EXPAND * a0 * dmax <= p.max_step;
+        };
+        // make (xa, fa, ga) the new iterate: history update, convergence tests
+        auto accept = [&](const double *xa, double fa, const double *ga) {
+            double ss = 0.0, yy = 0.0, sy = 0.0;
+            double dx[MTG_MAX_PARAMS], dg[MTG_MAX_PARAMS];
+            for (int k = 0; k < nd; ++k) {
+                dx[k] = xa[k] - s.X[(size_t)k * B + b]; dg[k] = ga[k] - s.G[(size_t)k * B + b];
+                ss += dx[k] * dx[k]; yy += dg[k] * dg[k]; sy += dx[k] * dg[k];
+            }
             if (sy > 1e-10 * sqrt(ss) * sqrt(yy) && sy > 0.0) {
                 const int slot = s.hist_head[b];
                 for (int k = 0; k < nd; ++k) { s.SH[((size_t)slot * nd + k) * B + b] = dx[k]; s.YH[((size_t)slot * nd + k) * B + b] = dg[k]; }
@@ -162,16 +191,35 @@ __global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__res
             }
             double pg = 0.0;
             for (int k = 0; k < nd; ++k) {
-                s.X[(size_t)k * B + b] = xt[k]; s.G[(size_t)k * B + b] = gt[k];
-                pg = fmax(pg, fabs(xt[k] - clampd(xt[k] - gt[k], p.lo[k], p.hi[k])));
+                s.X[(size_t)k * B + b] = xa[k]; s.G[(size_t)k * B + b] = ga[k];
+                pg = fmax(pg, fabs(xa[k] - clampd(xa[k] - ga[k], p.lo[k], p.hi[k])));
             }
-            s.F[b] = ft;
+            s.F[b] = fa;
             const int it = s.iter[b] + 1; s.iter[b] = it;
-            s.restarted[b] = 0;
+            s.restarted[b] = 0; s.has_cand[b] = 0; s.n_exp[b] = 0;
             if (pg <= p.gtol) { done = true; status = 0; }
-            else if ((F - ft) <= p.ftol * fmax(fmax(fabs(F), fabs(ft)), 1.0)) { done = true; status = 0; }
+            else if ((F - fa) <= p.ftol * fmax(fmax(fabs(F), fabs(fa)), 1.0)) { done = true; status = 0; }
             else if (it >= p.max_iter) { done = true; status = 1; }
             else need_dir = true;
+        };
+        auto store_candidate_and_expand = [&]() {
+            for (int k = 0; k < nd; ++k) { s.XC[(size_t)k * B + b] = xt[k]; s.GC[(size_t)k * B + b] = gt[k]; }
+            s.FC[b] = ft; s.has_cand[b] = 1; s.n_exp[b] += 1;
+            lbfgs_set_trial(s, p, b, LB_EXPAND * s.alpha[b]);
+        };
+        if (s.has_cand[b]) {
+            // this evaluation was an expansion trial; the stored candidate already satisfies Armijo
+            if (armijo_at && ft < s.FC[b]) {
+                if (wants_expansion()) store_candidate_and_expand();
+                else accept(xt, ft, gt);
+            } else {
+                double xc[MTG_MAX_PARAMS], gc[MTG_MAX_PARAMS];
+                for (int k = 0; k < nd; ++k) { xc[k] = s.XC[(size_t)k * B + b]; gc[k] = s.GC[(size_t)k * B + b]; }
+                accept(xc, s.FC[b], gc);
+            }
+        } else if (armijo_at) {
+            if (wants_expansion()) store_candidate_and_expand();
+            else accept(xt, ft, gt);
         } else {
             const int lc = s.ls_count[b] + 1; s.ls_count[b] = lc;
             if (lc >= p.max_ls) {
@@ -192,7 +240,7 @@ __global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__res
     if (need_dir) {
         double alpha;
         if (!lbfgs_direction(s, p, b, &alpha)) { done = true; status = 0; }
-        else { s.ls_count[b] = 0; lbfgs_set_trial(s, p, b, alpha); }
+        else { s.ls_count[b] = 0; s.n_exp[b] = 0; s.has_cand[b] = 0; lbfgs_set_trial(s, p, b, alpha); }
     }
     if (done) { s.status[b] = status; s.flags[b] = 0; }
 }
@@ -240,8 +288,8 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     // ---- one allocation for all state ---------------------------------------------------------
     const size_t Bz = (size_t)B;
     size_t nd_ = (size_t)nd;
-    size_t n_dbl = 3 * nd_ * Bz + 2 * (size_t)m * nd_ * Bz + (size_t)m * Bz + 3 * Bz + 2 * nd_ * Bz + Bz;
-    size_t n_int = 9 * Bz + 2 * Bz + 8;
+    size_t n_dbl = 3 * nd_ * Bz + 2 * (size_t)m * nd_ * Bz + (size_t)m * Bz + 3 * Bz + 2 * nd_ * Bz + Bz + 2 * nd_ * Bz + Bz;
+    size_t n_int = 11 * Bz + 2 * Bz + 8;
     size_t cub_bytes = 0;
     cub::CountingInputIterator<int32_t> iota(0);
     cub::DeviceSelect::Flagged((void *)nullptr, cub_bytes, iota, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, B, stream);
@@ -257,10 +305,12 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     s.SH = take_d((size_t)m * nd_ * Bz); s.YH = take_d((size_t)m * nd_ * Bz); s.RHO = take_d((size_t)m * Bz);
     s.F = take_d(Bz); s.alpha = take_d(Bz); s.gd = take_d(Bz);
     s.XT = take_d(nd_ * Bz); s.GT = take_d(nd_ * Bz); s.LL = take_d(Bz);
+    s.XC = take_d(nd_ * Bz); s.GC = take_d(nd_ * Bz); s.FC = take_d(Bz);
     int32_t *iptr = (int32_t *)dptr;
     auto take_i = [&](size_t n) { int32_t *r = iptr; iptr += n; return r; };
     s.hist_n = take_i(Bz); s.hist_head = take_i(Bz); s.ls_count = take_i(Bz); s.iter = take_i(Bz);
     s.phase = take_i(Bz); s.status = take_i(Bz); s.restarted = take_i(Bz); s.k2_status = take_i(Bz); s.flags = take_i(Bz);
+    s.has_cand = take_i(Bz); s.n_exp = take_i(Bz);
     int32_t *list_a = take_i(Bz), *list_b = take_i(Bz);
     int32_t *d_count = take_i(8);           // [0], [1]: ping-pong counts
     void *cub_tmp = (void *)(((uintptr_t)iptr + 255) & ~(uintptr_t)255);
@@ -269,9 +319,13 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     double *tape = nullptr;
     cudaError_t e = cudaMallocAsync((void **)&tape, mtg_k2_tape_bytes_per_series(pl, N) * (size_t)chunk, stream);
     if (e != cudaSuccess) { cudaFreeAsync(base, stream); return mtg_cuda_check(e, "cudaMallocAsync(tape)"); }
-    int32_t *h_count = nullptr;
-    e = cudaMallocHost((void **)&h_count, sizeof(int32_t));
-    if (e != cudaSuccess) { cudaFreeAsync(tape, stream); cudaFreeAsync(base, stream); return mtg_cuda_check(e, "cudaMallocHost"); }
+    // pinned word for the active count: one per host thread, kept for the life of the thread (cudaMallocHost /
+    // cudaFreeHost synchronise the device, which would serialise concurrently running fits on other streams)
+    static thread_local int32_t *h_count = nullptr;
+    if (!h_count) {
+        e = cudaMallocHost((void **)&h_count, sizeof(int32_t));
+        if (e != cudaSuccess) { h_count = nullptr; cudaFreeAsync(tape, stream); cudaFreeAsync(base, stream); return mtg_cuda_check(e, "cudaMallocHost"); }
+    }
 
     const dim3 blk(LB_THREADS);
     k_lbfgs_init<<<(B + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, p, x0, list_a);
@@ -279,10 +333,11 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     cudaMemcpyAsync(d_count, h_count, sizeof(int32_t), cudaMemcpyHostToDevice, stream);
     mtg_count_launch();
 
+    const bool debug = getenv("MTG_LBFGS_DEBUG") != nullptr;
     int bound = B;                          // host-side upper bound on the active count
     int32_t *list = list_a, *list_next = list_b;
     int32_t *cnt = d_count, *cnt_next = d_count + 1;
-    const long long max_rounds = (long long)p.max_iter * (p.max_ls + 1) + 2;
+    const long long max_rounds = (long long)p.max_iter * (p.max_ls + LB_MAX_EXPAND + 1) + 2;
     rc = 0;
     for (long long round = 0; round < max_rounds && bound > 0; ++round) {
         BatchArgs a{N, S, group, bound, t, y, diag, ds_mean, s.XT, s.LL, s.GT, s.k2_status, flags, list, cnt, nullptr};
@@ -297,6 +352,7 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
             cudaMemcpyAsync(h_count, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
             if ((rc = mtg_cuda_check(cudaStreamSynchronize(stream), "lbfgs round sync"))) break;
             bound = *h_count;
+            if (debug) fprintf(stderr, "[mtg_lbfgs] B=%d round %lld active %d\n", B, round + 1, bound);
         }
     }
     if (!rc) {
@@ -307,6 +363,5 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     cudaFreeAsync(tape, stream);
     cudaFreeAsync(base, stream);
     if (!rc) rc = mtg_cuda_check(cudaStreamSynchronize(stream), "lbfgs final sync");
-    cudaFreeHost(h_count);
     return rc;
 }

@@ -96,16 +96,22 @@ def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
 
 def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
                      extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
-                     max_iter=200, device=None, distributed=None, chunk=4096, return_lightcurves=False,
+                     max_iter=200, device=None, distributed=None, chunk=None, pipeline=3, return_lightcurves=False,
                      simulator_kwargs=None):
     """Simulate one lightcurve per row of ``null_samples`` (posterior draws of the null kernel's
     parameters) on the window of ``lightcurve`` and MLE-fit each with both kernels.
 
     ``null_slots``: positions in the alternative's parameter vector of the parameters it shares with the
     null model (default: the trailing ``len(null)`` ones when the alternative is ``extra + null`` as in the
-    tutorial, else the leading ones if names match).  Returns an ``LRTResult`` holding the arrays for ALL
-    simulations (gathered over ranks when ``torch.distributed`` is initialised)."""
+    tutorial, else the leading ones if names match).  The local simulations are cut into chunks of ``chunk``
+    (default: ``ceil(local / pipeline)`` clamped to 2048..8192) and up to ``pipeline`` chunks are in flight at once,
+    each on its own CUDA stream with its own simulator workspace: the few slowly converging fits that end every
+    batched L-BFGS (a latency-bound tail of ~1 ms rounds) then overlap the FFTs and the bulk of the other chunks'
+    fits instead of idling the GPU.  Returns an ``LRTResult`` holding the arrays for ALL simulations (gathered
+    over ranks when ``torch.distributed`` is initialised)."""
+    import concurrent.futures
     import torch
+    from .fitting import multistart_points
     lib = _native.lib()
     _native.require_device()
     dist = None
@@ -121,7 +127,8 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         rank, world = dist.get_rank(), dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    _native.check(lib.mtg_set_device(device.index if device.index is not None else 0))
+    dev_index = device.index if device.index is not None else 0
+    _native.check(lib.mtg_set_device(dev_index))
 
     null_samples = np.ascontiguousarray(np.atleast_2d(null_samples), dtype=np.float64)
     n_total = null_samples.shape[0]
@@ -140,74 +147,103 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         null_slots = list(range(nd1 - nd0, nd1)) if tail == [strip(s) for s in n0] and head != tail else list(range(nd0))
     x_alt0 = gp1.get_parameter_vector().copy()
 
-    sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor,
-                                   **(simulator_kwargs or {}))
-    h = sim._sim()
     N = lightcurve.n
     t_dev = torch.from_numpy(np.ascontiguousarray(lightcurve.times, dtype=np.float64)).to(device)
-    stream = torch.cuda.current_stream(device)
-    sp = stream.cuda_stream
-    rng = np.random.default_rng(seed + 7919 * rank)
     opts = _native.MtgLbfgsOpts(int(max_iter), 10, 2.220446049250313e-09, 1e-5, 20, 0)
+    pipeline = max(1, int(pipeline))
+    if chunk is None:
+        chunk = min(8192, max(2048, -(-L // pipeline)))        # small shards: one chunk (every extra chunk adds a tail)
+    chunk = max(1, int(chunk))
+    starts = list(range(0, L, chunk))
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    t_sim = t_null = t_alt = 0.0
     out_T = np.empty(L); out_l0 = np.empty(L); out_l1 = np.empty(L)
     out_p0 = np.empty((L, nd0)); out_p1 = np.empty((L, nd1)); out_s0 = np.empty(L, dtype=np.int32); out_s1 = np.empty(L, dtype=np.int32)
-    kept = []
-    for c0 in range(0, L, chunk):
-        Lc = min(chunk, L - c0)
-        p_dev = torch.from_numpy(np.ascontiguousarray(mine[c0:c0 + Lc])).to(device)
-        rates = torch.empty((N, Lc), dtype=torch.float64, device=device)
-        y = torch.empty_like(rates); dy = torch.empty_like(rates); diag = torch.empty_like(rates)
-        means = torch.empty(Lc, dtype=torch.float64, device=device)
-        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-        e0.record(stream)
-        _native.check(lib.mtg_sim_generate_dev(h, Lc, ctypes.byref(m0), p_dev.data_ptr(), None,
-                                               int(seed) * 1000003 + (i0 + c0), rates.data_ptr(), sp))
-        _native.check(lib.mtg_sim_add_noise_dev(h, Lc, rates.data_ptr(), int(seed) * 1000003 + 17 + (i0 + c0),
-                                                y.data_ptr(), dy.data_ptr(), sp))
-        _native.check(lib.mtg_prepare_data_dev(N, Lc, y.data_ptr(), dy.data_ptr(), diag.data_ptr(), means.data_ptr(), sp))
-        e1.record(stream)
-        # ---- null fits: start 0 = the generating parameters, others = 10 % Gaussian balls ----------------
-        from .fitting import multistart_points
-        x0 = multistart_points(mine[c0:c0 + Lc], list(zip(lo0, hi0)), n_starts_null, rng)
-        B0 = Lc * n_starts_null
-        x0_dev = torch.from_numpy(np.ascontiguousarray(x0)).to(device)
-        ox = torch.empty((B0, nd0), dtype=torch.float64, device=device); of = torch.empty(B0, dtype=torch.float64, device=device)
-        oi = torch.empty(B0, dtype=torch.int32, device=device); os_ = torch.empty(B0, dtype=torch.int32, device=device)
-        _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m0), N, Lc, n_starts_null, B0, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
-                                        means.data_ptr(), x0_dev.data_ptr(), ctypes.byref(opts), ox.data_ptr(), of.data_ptr(),
-                                        oi.data_ptr(), os_.data_ptr(), _native.FLAG_DS_MEAN, sp))
-        best0 = torch.empty(Lc, dtype=torch.float64, device=device); arg0 = torch.empty(Lc, dtype=torch.int32, device=device)
-        _native.check(lib.mtg_group_best_dev(Lc, n_starts_null, of.data_ptr(), best0.data_ptr(), arg0.data_ptr(), sp))
-        e2.record(stream)
-        a0 = arg0.cpu().numpy().astype(np.int64)
-        x_null = ox.cpu().numpy()[a0]
-        # ---- alternative fits ---------------------------------------------------------------------------------
-        x1 = alternative_starts(x_alt0, x_null, null_slots, lo1, hi1, n_starts_alt, rng).reshape(Lc * n_starts_alt, nd1)
-        B1 = Lc * n_starts_alt
-        x1_dev = torch.from_numpy(np.ascontiguousarray(x1)).to(device)
-        ax = torch.empty((B1, nd1), dtype=torch.float64, device=device); af = torch.empty(B1, dtype=torch.float64, device=device)
-        ai = torch.empty(B1, dtype=torch.int32, device=device); as_ = torch.empty(B1, dtype=torch.int32, device=device)
-        _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m1), N, Lc, n_starts_alt, B1, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
-                                        means.data_ptr(), x1_dev.data_ptr(), ctypes.byref(opts), ax.data_ptr(), af.data_ptr(),
-                                        ai.data_ptr(), as_.data_ptr(), _native.FLAG_DS_MEAN, sp))
-        best1 = torch.empty(Lc, dtype=torch.float64, device=device); arg1 = torch.empty(Lc, dtype=torch.int32, device=device)
-        _native.check(lib.mtg_group_best_dev(Lc, n_starts_alt, af.data_ptr(), best1.data_ptr(), arg1.data_ptr(), sp))
-        e3.record(stream)
-        torch.cuda.synchronize(device)
-        t_sim += e0.elapsed_time(e1); t_null += e1.elapsed_time(e2); t_alt += e2.elapsed_time(e3)
-        a1 = arg1.cpu().numpy().astype(np.int64)
-        sl = slice(c0, c0 + Lc)
-        out_l0[sl] = -best0.cpu().numpy(); out_l1[sl] = -best1.cpu().numpy()
-        out_p0[sl] = x_null; out_p1[sl] = ax.cpu().numpy()[a1]
-        out_s0[sl] = os_.cpu().numpy()[a0]; out_s1[sl] = as_.cpu().numpy()[a1]
-        if return_lightcurves:
-            kept.append((y.cpu().numpy().T.copy(), dy.cpu().numpy().T.copy()))
-    sim.close()
+    kept = {}
+    times = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    main_stream = torch.cuda.current_stream(device)
+
+    def worker(slot_chunks):
+        """One pipeline slot: its own stream and simulator workspace, chunks processed in order."""
+        torch.cuda.set_device(device)
+        _native.check(lib.mtg_set_device(dev_index))
+        stream = torch.cuda.Stream(device) if len(starts) > 1 else main_stream
+        stream.wait_stream(main_stream)
+        sp = stream.cuda_stream
+        sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor,
+                                       **(simulator_kwargs or {}))
+        h = sim._sim()
+        local = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0}
+        try:
+            with torch.cuda.stream(stream):
+                for c0 in slot_chunks:
+                    Lc = min(chunk, L - c0)
+                    rng = np.random.default_rng([int(seed), int(rank), int(c0)])
+                    p_dev = torch.from_numpy(np.ascontiguousarray(mine[c0:c0 + Lc])).to(device)
+                    rates = torch.empty((N, Lc), dtype=torch.float64, device=device)
+                    y = torch.empty_like(rates); dy = torch.empty_like(rates); diag = torch.empty_like(rates)
+                    means = torch.empty(Lc, dtype=torch.float64, device=device)
+                    e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+                    e0.record(stream)
+                    _native.check(lib.mtg_sim_generate_dev(h, Lc, ctypes.byref(m0), p_dev.data_ptr(), None,
+                                                           int(seed) * 1000003 + (i0 + c0), rates.data_ptr(), sp))
+                    _native.check(lib.mtg_sim_add_noise_dev(h, Lc, rates.data_ptr(), int(seed) * 1000003 + 17 + (i0 + c0),
+                                                            y.data_ptr(), dy.data_ptr(), sp))
+                    _native.check(lib.mtg_prepare_data_dev(N, Lc, y.data_ptr(), dy.data_ptr(), diag.data_ptr(), means.data_ptr(), sp))
+                    e1.record(stream)
+                    # ---- null fits: start 0 = the generating parameters, others = 10 % Gaussian balls ------------
+                    x0 = multistart_points(mine[c0:c0 + Lc], list(zip(lo0, hi0)), n_starts_null, rng)
+                    B0 = Lc * n_starts_null
+                    x0_dev = torch.from_numpy(np.ascontiguousarray(x0)).to(device)
+                    ox = torch.empty((B0, nd0), dtype=torch.float64, device=device); of = torch.empty(B0, dtype=torch.float64, device=device)
+                    oi = torch.empty(B0, dtype=torch.int32, device=device); os_ = torch.empty(B0, dtype=torch.int32, device=device)
+                    _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m0), N, Lc, n_starts_null, B0, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
+                                                    means.data_ptr(), x0_dev.data_ptr(), ctypes.byref(opts), ox.data_ptr(), of.data_ptr(),
+                                                    oi.data_ptr(), os_.data_ptr(), _native.FLAG_DS_MEAN, sp))
+                    best0 = torch.empty(Lc, dtype=torch.float64, device=device); arg0 = torch.empty(Lc, dtype=torch.int32, device=device)
+                    _native.check(lib.mtg_group_best_dev(Lc, n_starts_null, of.data_ptr(), best0.data_ptr(), arg0.data_ptr(), sp))
+                    e2.record(stream)
+                    a0 = arg0.cpu().numpy().astype(np.int64)
+                    x_null = ox.cpu().numpy()[a0]
+                    # ---- alternative fits ---------------------------------------------------------------------------
+                    x1 = alternative_starts(x_alt0, x_null, null_slots, lo1, hi1, n_starts_alt, rng).reshape(Lc * n_starts_alt, nd1)
+                    B1 = Lc * n_starts_alt
+                    x1_dev = torch.from_numpy(np.ascontiguousarray(x1)).to(device)
+                    ax = torch.empty((B1, nd1), dtype=torch.float64, device=device); af = torch.empty(B1, dtype=torch.float64, device=device)
+                    ai = torch.empty(B1, dtype=torch.int32, device=device); as_ = torch.empty(B1, dtype=torch.int32, device=device)
+                    _native.check(lib.mtg_lbfgs_dev(ctypes.byref(m1), N, Lc, n_starts_alt, B1, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(),
+                                                    means.data_ptr(), x1_dev.data_ptr(), ctypes.byref(opts), ax.data_ptr(), af.data_ptr(),
+                                                    ai.data_ptr(), as_.data_ptr(), _native.FLAG_DS_MEAN, sp))
+                    best1 = torch.empty(Lc, dtype=torch.float64, device=device); arg1 = torch.empty(Lc, dtype=torch.int32, device=device)
+                    _native.check(lib.mtg_group_best_dev(Lc, n_starts_alt, af.data_ptr(), best1.data_ptr(), arg1.data_ptr(), sp))
+                    e3.record(stream)
+                    stream.synchronize()
+                    local["simulate_ms"] += e0.elapsed_time(e1); local["fit_null_ms"] += e1.elapsed_time(e2); local["fit_alt_ms"] += e2.elapsed_time(e3)
+                    a1 = arg1.cpu().numpy().astype(np.int64)
+                    sl = slice(c0, c0 + Lc)
+                    out_l0[sl] = -best0.cpu().numpy(); out_l1[sl] = -best1.cpu().numpy()
+                    out_p0[sl] = x_null; out_p1[sl] = ax.cpu().numpy()[a1]
+                    out_s0[sl] = os_.cpu().numpy()[a0]; out_s1[sl] = as_.cpu().numpy()[a1]
+                    if return_lightcurves:
+                        kept[c0] = (y.cpu().numpy().T.copy(), dy.cpu().numpy().T.copy())
+        finally:
+            sim.close()
+        return local
+
+    n_slots = min(pipeline, len(starts))
+    slots = [starts[k::n_slots] for k in range(n_slots)]
+    if n_slots <= 1:
+        results = [worker(slots[0])] if slots else []
+    else:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=n_slots) as ex:
+            results = list(ex.map(worker, slots))
+    torch.cuda.synchronize(device)
+    for r in results:
+        for k in times:
+            times[k] += r[k]
     out_T[:] = lrt_statistic(out_l0, out_l1)
-    timings = {"simulate_ms": t_sim, "fit_null_ms": t_null, "fit_alt_ms": t_alt, "n_local": L}
+    timings = dict(times, n_local=L, chunk=chunk, pipeline=n_slots,
+                   note="per-stage device times are summed over concurrently running chunks")
 
     if dist is not None and world > 1:
         pack = np.empty((L, 5 + nd0 + nd1))
@@ -219,5 +255,6 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     else:
         res = LRTResult(out_T, out_l0, out_l1, out_p0, out_p1, out_s0, out_s1, timings)
     if return_lightcurves:
-        res.lightcurves = (np.concatenate([k[0] for k in kept]), np.concatenate([k[1] for k in kept])) if kept else None
+        ks = sorted(kept)
+        res.lightcurves = (np.concatenate([kept[k][0] for k in ks]), np.concatenate([kept[k][1] for k in ks])) if ks else None
     return res
