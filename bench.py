@@ -158,7 +158,180 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank):
+def lrt_problem():
+    from mind_the_gaps_b200.lightcurves import GappyLightcurve
+    from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+    from helpers import c2_truth, window
+    tt_, exposures = window(N_POINTS, 2)
+    lc = GappyLightcurve(tt_, np.full(N_POINTS, 0.5), np.full(N_POINTS, 0.02), exposures)
+    tr = c2_truth()
+    b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    null_k = DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
+    alt_k = Lorentzian(tr[2] - 2, np.log(20.0), tr[4], bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
+        DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
+    return lc, null_k, alt_k, tr
+
+
+def lrt_measurement(torch, rank, world, n_sims):
+    """Whole-job LRT throughput: ``n_sims`` simulations in total, rank r simulates and fits its shard; results are
+    all-gathered (NCCL) inside the timed region.  Wall clock bracketed by barriers, max over ranks."""
+    import torch.distributed as dist
+    from mind_the_gaps_b200 import lrt
+    lc, null_k, alt_k, tr = lrt_problem()
+    samples = tr[None, :2] + np.random.default_rng(5).normal(0, 0.1, (n_sims, 2))
+    runs = {}
+    res = None
+    for mode in ("exact", "fast"):
+        kw = dict(n_starts_null=2, n_starts_alt=8, seed=3, distributed=(world > 1), simulator_kwargs={"fft_length": mode})
+        lrt.simulate_and_fit(lc, null_k, alt_k, samples[:min(n_sims, 256 * world)], **kw)      # warm-up: plans, pools, clocks
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = lrt.simulate_and_fit(lc, null_k, alt_k, samples, **kw)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            w = torch.tensor([wall], dtype=torch.float64, device="cuda"); dist.all_reduce(w, op=dist.ReduceOp.MAX); wall = float(w.item())
+        runs[mode] = {"wall_s": wall, "sims_per_s": n_sims / wall,
+                      "rank0_stage_ms": {k: v for k, v in res.timings.items() if k != "note"},
+                      "n_fft": int(lc.get_simulator(null_k.get_psd, extension_factor=2, fft_length=mode).fftndatapoints)}
+    return {"sims_total": n_sims, "sims_per_gpu": -(-n_sims // world), "scaling": "strong", "starts": {"null": 2, "alt": 8},
+            "fft_length": runs, "note": "exact = the reference's grid length (a prime here -> Bluestein FFT); fast = opt-in 7-smooth length",
+            "wall_s": runs["exact"]["wall_s"], "sims_per_s": runs["exact"]["sims_per_s"],
+            "T_median": float(np.median(res.T)), "T_p95": float(np.percentile(res.T, 95)),
+            "all_finite": bool(np.all(np.isfinite(res.T))), "n_results": int(len(res.T))}
+
+
+def c5_workload(n_points=100000, seed=6):
+    rng = np.random.default_rng(seed)
+    t = np.cumsum(rng.uniform(0.5, 1.5, n_points)) * 600.0              # regular-ish 10-minute cadence
+    y = 1.0 + 0.05 * np.cumsum(rng.normal(0, 0.05, n_points)) + rng.normal(0, 0.01, n_points)
+    dy = np.full(n_points, 0.01)
+    return t, y, dy
+
+
+def c5_kernel():
+    from mind_the_gaps_b200.celerite import terms
+    day = 86400.0
+    w = lambda d: float(np.log(2 * np.pi / (d * day)))
+    b = dict(log_S0=(-30, 10), log_Q=(np.log(0.51), 8), log_omega0=(-20, 0))
+    return (terms.SHOTerm(-9.0, np.log(3.0), w(30.0), bounds=b) + terms.SHOTerm(-10.0, np.log(8.0), w(7.0), bounds=b)
+            + terms.SHOTerm(-11.0, np.log(20.0), w(1.5), bounds=b) + terms.RealTerm(-8.0, w(200.0), bounds=dict(log_a=(-30, 10), log_c=(-25, 0))))
+
+
+def c5_measurement(torch, lib, _native, dev, stream, timed, rank, world, n_points=100000, n_sets=100000):
+    from mind_the_gaps_b200.celerite import GP
+    t, y, dy = c5_workload(n_points)
+    kernel = c5_kernel()
+    gp = GP(kernel, mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    model = gp.device_model()
+    B = -(-n_sets // world)
+    p0 = gp.get_parameter_vector()
+    p = p0[None, :] + np.random.default_rng(7 + rank).normal(0, 0.1, (B, len(p0)))
+    d_t = torch.from_numpy(t).to(dev); d_y = torch.from_numpy(y).to(dev); d_d = torch.from_numpy((dy + 1e-12) ** 2).to(dev)
+    d_p = torch.from_numpy(p).to(dev)
+    ll = torch.empty(B, dtype=torch.float64, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def k1():
+        _native.check(lib.mtg_loglike_dev(ctypes.byref(model), n_points, 1, B, B, d_t.data_ptr(), d_y.data_ptr(), d_d.data_ptr(), None,
+                                          d_p.data_ptr(), ll.data_ptr(), st.data_ptr(), _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
+    ms = timed(k1, 2)
+    J = 7
+    flops = n_points * (4 * J * J + 12 * J + 5)
+    ok = bool(torch.isfinite(ll).all().item())
+    return {"n_points": n_points, "j": J, "ndim": int(len(p0)), "parameter_sets_per_gpu": B, "ms": ms, "evals_per_s_per_gpu": B / (ms * 1e-3),
+            "tflops_algorithmic_per_gpu": B * flops / (ms * 1e-3) / 1e12, "all_finite": ok,
+            "status_counts": [int(x) for x in torch.bincount(st, minlength=4).tolist()]}
+
+
+def c3_measurement(torch, rank, world, n_lc=10000, n_e13=64):
+    """Simulator ensemble on the 1000-point gapped window: n_lc TK95 lightcurves + Poisson noise over the ranks, and a
+    bounded E13 (lognormal) + Kraft sample."""
+    from mind_the_gaps_b200.lightcurves import GappyLightcurve
+    from mind_the_gaps_b200.models import psd_models
+    from helpers import window
+    day = 86400.0
+    tt_, exposures = window(N_POINTS, 3)
+    mine = -(-n_lc // world)
+    out = {}
+    lc = GappyLightcurve(tt_, np.full(N_POINTS, 0.5), np.full(N_POINTS, 0.02), exposures)
+    psd = psd_models.BendingPowerlaw(S0=(0.1 * 0.5) ** 2, omega0=2 * np.pi / (20 * day))
+    for mode in ("exact", "fast"):
+        sim = lc.get_simulator(psd, "Gaussian", extension_factor=2, fft_length=mode)
+        sim.generate_lightcurves(64, seed=1)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        rates = sim.generate_lightcurves(mine, seed=4)
+        noisy, dy = sim.add_noise(rates, seed=5)
+        torch.cuda.synchronize(); wall = time.perf_counter() - t0
+        n_fft = int(sim.fftndatapoints)
+        out["tk95_poisson_" + mode] = {"lightcurves_per_gpu": mine, "wall_s": wall, "lightcurves_per_s_per_gpu": mine / wall, "n_fft": n_fft,
+                                       "algorithmic_GBps": mine * (24.0 * n_fft + 8.0 * n_fft / 2) / wall / 1e9,
+                                       "finite": bool(np.all(np.isfinite(noisy)))}
+        sim.close()
+    lc2 = GappyLightcurve(tt_, np.full(N_POINTS, 0.01), np.full(N_POINTS, 0.002), exposures, bkg_rate=np.full(N_POINTS, 0.001),
+                          bkg_rate_err=np.full(N_POINTS, 1e-4))
+    psd2 = psd_models.BendingPowerlaw(S0=(0.3 * 0.01) ** 2, omega0=2 * np.pi / (20 * day))
+    sim = lc2.get_simulator(psd2, "Lognormal", extension_factor=2, fft_length="fast", max_iter=400)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim.generate_lightcurves(4, seed=1)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        rates, info = sim.generate_lightcurves(n_e13, seed=4, return_info=True)
+        noisy, dy = sim.add_noise(rates, seed=5)
+        torch.cuda.synchronize(); wall = time.perf_counter() - t0
+    out["e13_lognormal_kraft_fast"] = {"lightcurves": n_e13, "wall_s": wall, "lightcurves_per_s_per_gpu": n_e13 / wall,
+                                       "e13_iterations_mean": float(np.mean(info["e13_iterations"])), "noise": sim.noise.name,
+                                       "finite": bool(np.all(np.isfinite(noisy)))}
+    sim.close()
+    return out
+
+
+def cpu_lrt_rate(n_sims=2):
+    """The reference's LRT algorithm on ONE host core (tutorial_ppp.ipynb cells 11-15 without the MCMC refinement, i.e.
+    flattering to the CPU): numpy TK95 + binning + Poisson noise (oracle.simulator), then scipy L-BFGS-B with
+    finite-difference gradients (as GPModelling.fit) on the C restatement of celerite, null (1 start) and alternative (1 start)."""
+    from scipy.optimize import minimize
+    from oracle import cref, simulator as osim, terms as oterms
+    from helpers import c2_truth, window
+    tt_, exposures = window(N_POINTS, 2)
+    tr = c2_truth()
+    cfg = osim.setup(tt_, exposures, aliasing_factor=2, extension_factor=2)
+    rng = np.random.default_rng(11)
+    M = cfg["n_fft"] // 2 + 1
+    psd = lambda w: oterms.psd([("drw",)], tr[:2], w)
+    t0 = time.perf_counter()
+    evals = 0
+    for _ in range(n_sims):
+        re, im = rng.normal(size=(2, M))
+        full = osim.simulate_regular(cfg["n_fft"], cfg["sim_dt"], psd, 0.5, re, im)
+        i0, i1, shift = osim.cut_segment(cfg["grid"], cfg["sim_dt"], cfg["sim_duration"], cfg["strategy"][0][0], rng.random())
+        tseg = cfg["grid"][i0:i1] + shift
+        lo = np.searchsorted(tseg, [s[0] for s in cfg["strategy"]]); hi = np.searchsorted(tseg, [s[1] for s in cfg["strategy"]])
+        rates = np.array([full[i0 + a:i0 + b].mean() for a, b in zip(lo, hi)])          # same bins as the reference's O(N N_seg) mask loop
+        counts = rng.poisson(np.clip(rates, 0, None) * exposures)
+        y, dy = osim.poisson_noise(rates, exposures, np.zeros(N_POINTS), np.zeros(N_POINTS), counts)
+        dy = np.maximum(dy, 1e-6)
+        for spec, x0, bounds in (([("drw",)], tr[:2], [(-15, 5), (-20, -5)]),
+                                 ([("lorentzian",), ("drw",)], np.r_[tr[2] - 2, np.log(20.0), tr[4], tr[:2]],
+                                  [(-20, 5), (0.5, 7), (-16, -9), (-15, 5), (-20, -5)])):
+            cnt = [0]
+
+            def nll(p):
+                cnt[0] += 1
+                v = -cref.loglike_params(spec, p[None, :], tt_, y, dy, nthreads=1)[0]
+                return v if np.isfinite(v) else 1e25
+            minimize(nll, x0, method="L-BFGS-B", bounds=bounds)
+            evals += cnt[0]
+    dt = time.perf_counter() - t0
+    return n_sims / dt, dt, evals / n_sims
+
+
+def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank, world, args):
     """K2 (loglike + gradient) throughput, the latency-bound 64-walker call of config C2 as emcee would
     issue it, and a short LRT (simulate + fit null + fit alternative) -- reported under "extras"."""
     out = {}
@@ -170,17 +343,18 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
             fn()
         e1.record(stream); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
-    # K2: 64 walkers x 1024 ensembles (tape 7.3 GB)
-    Bg = WALKERS * 1024
+    # K2 (log-likelihood + gradient): 64 walkers x 2368 ensembles = 4 full waves of 148 SMs x 2 CTAs x 128 threads
+    Bg = WALKERS * 2368
+    if Bg > d_p.shape[0]:
+        Bg = d_p.shape[0]
     g_ll = torch.empty(Bg, dtype=torch.float64, device=dev); g_g = torch.empty((Bg, 5), dtype=torch.float64, device=dev)
     g_st = torch.empty(Bg, dtype=torch.int32, device=dev)
     def k2():
         _native.check(lib.mtg_loglike_grad_dev(ctypes.byref(model), N_POINTS, 1, Bg, Bg, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(),
                                                None, d_p.data_ptr(), g_ll.data_ptr(), g_g.data_ptr(), g_st.data_ptr(), 0, stream.cuda_stream))
     ms = timed(k2, 3)
-    tape_bytes = Bg * N_POINTS * 14 * 8
-    out["loglike_grad"] = {"batch": Bg, "ms": ms, "evals_per_s": Bg / (ms * 1e-3), "tape_GB_written_and_read": 2 * tape_bytes / 1e9,
-                           "tape_GBps": 2 * tape_bytes / (ms * 1e-3) / 1e9}
+    out["loglike_grad"] = {"batch": Bg, "ms": ms, "evals_per_s": Bg / (ms * 1e-3),
+                           "note": "forward + segment replay into shared memory + adjoint sweep; no O(N) tape in HBM"}
     # the 32-parameter-set half-ensemble call of a 64-walker emcee step (latency bound by construction)
     s_ll = torch.empty(32, dtype=torch.float64, device=dev); s_st = torch.empty(32, dtype=torch.int32, device=dev)
     def k1_small():
@@ -188,35 +362,22 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
                                           d_p.data_ptr(), s_ll.data_ptr(), s_st.data_ptr(), _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
     ms = timed(k1_small, 20)
     out["half_ensemble_of_64_walkers"] = {"batch": 32, "ms": ms, "evals_per_s": 32 / (ms * 1e-3)}
-    # a short LRT: DRW null vs Lorentzian + DRW alternative on the same 1000-point window
+    # ---- config C4: the full Protassov LRT, 10^4 simulations (DRW null vs Lorentzian + DRW alternative, N = 1000), sharded
+    #      over the ranks (strong scaling: the total is fixed); simulate + fit null + fit alternative per simulation
     try:
-        from mind_the_gaps_b200 import lrt
-        from mind_the_gaps_b200.lightcurves import GappyLightcurve
-        from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
-        from helpers import c2_truth, window
-        tt_, exposures = window(N_POINTS, 2)
-        lc = GappyLightcurve(tt_, np.full(N_POINTS, 0.5), np.full(N_POINTS, 0.02), exposures)
-        tr = c2_truth()
-        b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
-        null_k = DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
-        alt_k = Lorentzian(tr[2] - 2, np.log(20.0), tr[4], bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
-            DampedRandomWalk(tr[0], tr[1], bounds=b_drw)
-        n_sims = 2048
-        samples = tr[None, :2] + np.random.default_rng(5 + rank).normal(0, 0.1, (n_sims, 2))
-        runs = {}
-        for mode in ("exact", "fast"):
-            t0 = time.perf_counter()
-            res = lrt.simulate_and_fit(lc, null_k, alt_k, samples, n_starts_null=2, n_starts_alt=8, seed=3, distributed=False,
-                                       simulator_kwargs={"fft_length": mode})
-            wall = time.perf_counter() - t0
-            runs[mode] = {"wall_s": wall, "sims_per_s": n_sims / wall, "timings_ms": res.timings,
-                          "n_fft": int(lc.get_simulator(null_k.get_psd, extension_factor=2, fft_length=mode).fftndatapoints)}
-        out["lrt"] = {"sims": n_sims, "fft_length": runs, "note": "exact = the reference's grid length (prime here -> Bluestein FFT); fast = opt-in 7-smooth length",
-                      "wall_s": wall, "sims_per_s": n_sims / wall,
-                      "starts": {"null": 2, "alt": 8}, "timings_ms": res.timings, "T_median": float(np.median(res.T)),
-                      "T_p95": float(np.percentile(res.T, 95)), "all_finite": bool(np.all(np.isfinite(res.T)))}
+        out["lrt"] = lrt_measurement(torch, rank, world, args.lrt_sims)
     except Exception as exc:          # secondary: never fail the headline line
         out["lrt"] = {"error": repr(exc)}
+    # ---- config C5: N = 1e5 points, 3 x SHOTerm + RealTerm (J = 7), 1e5 parameter sets over the ranks, shared data
+    try:
+        out["c5_long_baseline_sweep"] = c5_measurement(torch, lib, _native, dev, stream, timed, rank, world)
+    except Exception as exc:
+        out["c5_long_baseline_sweep"] = {"error": repr(exc)}
+    # ---- config C3: simulator ensemble (TK95 Gaussian + Poisson; E13 lognormal + Kraft on a bounded sample)
+    try:
+        out["c3_simulator"] = c3_measurement(torch, rank, world)
+    except Exception as exc:
+        out["c3_simulator"] = {"error": repr(exc)}
     return out
 
 
@@ -231,6 +392,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (gradient, small batch, LRT)")
     ap.add_argument("--ref-sample", type=int, default=65536, help="parameter sets per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lrt-sims", type=int, default=10000, help="total simulations of the LRT leg (config C4), sharded over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -322,7 +484,7 @@ def main():
     # ---- secondary measurements (outside the timed region of the headline metric) ----------------
     extras = {}
     if not args.no_extras:
-        extras = secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank)
+        extras = secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank, world, args)
 
     tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -375,6 +537,15 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": "%d of the same parameter sets in %.1f s, oracle/celerite_ref.c "
                                               "(C restatement of celerite, OpenMP)" % (n, dt)}
+            if not args.no_extras:
+                try:
+                    r1, dt1, ev = cpu_lrt_rate(2)
+                    line["cpu_baseline"]["lrt"] = {"sims_per_s_one_core": r1, "sims_per_s_all_cores_if_perfectly_parallel": r1 * cores,
+                                                   "cores": cores, "sample": "2 simulations in %.1f s on one core: numpy TK95 + scipy L-BFGS-B "
+                                                   "(finite differences, 1 start per model, no MCMC refinement) on oracle/celerite_ref.c; "
+                                                   "%.0f likelihood evaluations per simulation" % (dt1, ev)}
+                except Exception as exc:
+                    line["cpu_baseline"]["lrt"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

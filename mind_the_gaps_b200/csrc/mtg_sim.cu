@@ -91,9 +91,68 @@ __device__ __forceinline__ double psd_eval(const PsdCoef &c, double w)
     return 0.79788456080286535588 * p;          // sqrt(2/pi)
 }
 
+// ---- fast helpers for the Philox path of K3 (statistical equivalence only; the injected-noise path keeps IEEE ops) ----
+// Standard normal pair from 128 Philox bits by Box-Muller with FP32 transcendentals.  ln(u1) keeps the full tail of a
+// 64-bit uniform: u1 = 2^-(z+1) * 1.m with z = leading zeros of the 64 random bits (geometric), m the next 23 bits, so
+// -2 ln u1 = 2 ln2 ((z + 1) - log2(1.m)) reaches ~9.4 sigma although every floating-point step is single precision
+// (relative error of a deviate ~1e-7: irrelevant for a random draw, ~6x fewer issue slots than the FP64 libm calls).
+__device__ __forceinline__ float2 philox_normal2_f32(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
+{
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)(item >> 32), draw, purpose),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint64_t bits = ((uint64_t)r.x << 32) | r.y;
+    const int z = bits ? __clzll((long long)bits) : 63;
+    const uint64_t norm = bits << z;                                   // top bit set (or 0)
+    const float mant = __uint_as_float(0x3f800000u | (uint32_t)((norm >> 40) & 0x7fffffu));       // [1, 2)
+    const float neg_log2_u = (float)(z + 1) - __log2f(mant) + 2.0e-8f;                     // > 0
+    const float rad = sqrtf(1.3862943611198906f * neg_log2_u);                              // sqrt(-2 ln u1)
+    const float ang = (float)(r.z >> 8) * 5.9604644775390625e-08f;                          // [0, 1) in steps of 2^-24
+    float sn, cs;
+    sincospif(2.0f * ang + 5.9604644775390625e-08f, &sn, &cs);
+    (void)r.w;
+    return make_float2(rad * cs, rad * sn);
+}
+// 1/x and sqrt(x) for x in the single-precision range from an FP32 seed + two Newton steps (<= 2 ulp); IEEE otherwise
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    if (!(fabs(x) > 1e-30 && fabs(x) < 1e30)) return 1.0 / x;
+    double y = (double)(1.0f / (float)x);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return fma(y, fma(-x, y, 1.0), y);
+}
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    if (!(x > 1e-30 && x < 1e30)) return sqrt(x);
+    double y = (double)rsqrtf((float)x);                 // ~ 1/sqrt(x)
+    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
+    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
+    const double g = x * y;                              // sqrt(x), then one correction step
+    return fma(0.5 * y, fma(-g, g, x), g);
+}
+__device__ __forceinline__ double psd_eval_fast(const PsdCoef &c, double w)
+{
+    const double w2 = w * w;
+    double p = 0.0;
+    for (int j = 0; j < c.nr; ++j) p += c.ar[j] * c.cr[j] * fast_rcp(c.cr[j] * c.cr[j] + w2);
+    for (int j = 0; j < c.nc; ++j) {
+        const double a = c.ac[j], b = c.bc[j], cc = c.cc[j], d = c.dc[j];
+        const double w02 = cc * cc + d * d;
+        p += ((a * cc + b * d) * w02 + (a * cc - b * d) * w2) * fast_rcp(w2 * w2 + 2.0 * (cc * cc - d * d) * w2 + w02 * w02);
+    }
+    return 0.79788456080286535588 * p;          // sqrt(2/pi)
+}
+
+static inline void spectrum_scales(int n_fft, double sim_dt, double *val, double *fold)
+{
+    volatile double nd = (double)n_fft * sim_dt;             // volatile: no host-side contraction / reassociation
+    *val = 1.0 / nd;
+    volatile double arg = nd * 2.5066282746310002;
+    *fold = sqrt(arg) / nd;
+}
+
 // K3: one thread per (frequency k, lightcurve l).  spec[l][k], k = 0..M-1.
 __global__ void __launch_bounds__(256)
-k_spectrum(int L, int n_fft, int M, double sim_dt, const PsdCoef *__restrict__ coefs,
+k_spectrum(int L, int n_fft, int M, double val, double fold, const PsdCoef *__restrict__ coefs,
            const double *__restrict__ psd_table, const double *__restrict__ normals, uint64_t seed,
            uint64_t lc_offset, double2 *__restrict__ spec)
 {
@@ -105,17 +164,22 @@ k_spectrum(int L, int n_fft, int M, double sim_dt, const PsdCoef *__restrict__ c
     if (k >= M) return;
     double2 out = make_double2(0.0, 0.0);
     if (k > 0) {
-        // np.fft.rfftfreq(N, dt) * 2 * np.pi  ==  ((k * (1/(N dt))) * 2) * pi
-        const double val = 1.0 / ((double)n_fft * sim_dt);
+        // np.fft.rfftfreq(N, dt) * 2 * np.pi  ==  ((k * (1/(N dt))) * 2) * pi ; val = 1/(N dt) and the scale
+        // fold = sqrt(N dt sqrt(2 pi)) / (N dt)  [rate = irfft(X) sqrt(N dt sqrt(2 pi)) / dt, numpy's irfft = Z2D / N,
+        // simulator.py:386-391] are IEEE double results computed once on the host (spectrum_scales)
         const double w = (((double)k * val) * 2.0) * 3.141592653589793;
-        const double psd = coefs ? psd_eval(sc, w) : psd_table[k];
-        double re, im;
-        if (normals) { re = normals[((size_t)l * 2) * M + k]; im = normals[((size_t)l * 2 + 1) * M + k]; }
-        else { const double2 z = philox_normal2(seed, 0u, (lc_offset + l) * (uint64_t)M + k, 0u); re = z.x; im = z.y; }
-        // rate = irfft(X) sqrt(N dt sqrt(2 pi)) / dt, numpy's irfft = Z2D / N  (simulator.py:386-391)
-        const double fold = sqrt((double)n_fft * sim_dt * 2.5066282746310002) / ((double)n_fft * sim_dt);
-        const double amp = sqrt(0.5 * psd) * fold;
-        out.x = re * amp; out.y = im * amp;
+        if (normals) {
+            // parity path: the reference's operations in IEEE arithmetic on the injected normals
+            const double psd = coefs ? psd_eval(sc, w) : psd_table[k];
+            const double re = normals[((size_t)l * 2) * M + k], im = normals[((size_t)l * 2 + 1) * M + k];
+            const double amp = sqrt(0.5 * psd) * fold;
+            out.x = re * amp; out.y = im * amp;
+        } else {
+            const double psd = coefs ? psd_eval_fast(sc, w) : psd_table[k];
+            const float2 z = philox_normal2_f32(seed, 0u, (lc_offset + l) * (uint64_t)M + k, 0u);
+            const double amp = fast_sqrt(0.5 * psd) * fold;
+            out.x = (double)z.x * amp; out.y = (double)z.y * amp;
+        }
         if ((n_fft % 2 == 0) && k == M - 1) out.y = 0.0;          // Nyquist bin is real (simulator.py:499-500)
     }
     // k == 0: the reference sets an arbitrary DC (1e6) and removes the mean afterwards
@@ -494,8 +558,10 @@ int sim_generate_core(Sim *s, int L, const mtg_model_t *model, const double *d_p
             k_psd_coeffs<<<(Lc + 127) / 128, 128, 0, stream>>>(pl, d_params + (size_t)l0 * pl.n_free, Lc, s->d_coef);
             mtg_count_launch();
         }
+        double sp_val, sp_fold;
+        spectrum_scales(n_fft, s->cfg.sim_dt, &sp_val, &sp_fold);
         k_spectrum<<<dim3((M + 255) / 256, Lc), 256, 0, stream>>>(
-            Lc, n_fft, M, s->cfg.sim_dt, model ? s->d_coef : nullptr, d_psd_table,
+            Lc, n_fft, M, sp_val, sp_fold, model ? s->d_coef : nullptr, d_psd_table,
             d_normals ? d_normals + (size_t)l0 * 2 * M : nullptr, seed, (uint64_t)l0, s->d_spec);
         mtg_count_launch();
         cufftHandle plan;
@@ -713,7 +779,9 @@ extern "C" int mtg_sim_regular_host(void *sim, int L, const mtg_model_t *model, 
         const int Lc = L - l0 < chunk ? L - l0 : chunk;
         if (normals) { cudaFree(d_nrm); d_nrm = nullptr; rc = upload(&d_nrm, normals + (size_t)l0 * 2 * M, (size_t)Lc * 2 * M, st); if (rc) break; }
         if (model) { k_psd_coeffs<<<(Lc + 127) / 128, 128, 0, st>>>(pl, d_par + (size_t)l0 * pl.n_free, Lc, s->d_coef); mtg_count_launch(); }
-        k_spectrum<<<dim3((M + 255) / 256, Lc), 256, 0, st>>>(Lc, n_fft, M, s->cfg.sim_dt, model ? s->d_coef : nullptr, d_tab,
+        double sp_val, sp_fold;
+        spectrum_scales(n_fft, s->cfg.sim_dt, &sp_val, &sp_fold);
+        k_spectrum<<<dim3((M + 255) / 256, Lc), 256, 0, st>>>(Lc, n_fft, M, sp_val, sp_fold, model ? s->d_coef : nullptr, d_tab,
                                                               d_nrm, seed, (uint64_t)l0, s->d_spec);
         cufftHandle plan;
         if ((rc = sim_get_plan(s, s->plans, CUFFT_Z2D, n_fft, Lc, &plan))) break;
