@@ -251,6 +251,31 @@ int mtg_group_best_dev(int S, int group, const double *f, double *best, int32_t 
 int mtg_predict_host(const mtg_model_t *model, int N, const double *t, const double *y, const double *diag,
                      const double *params, double *out_mu, double *out_var);
 
+/* ---- K8: device-resident affine-invariant ensemble sampler ------------------------------------
+ * Replaces the emcee 3.1.4 loop GPModelling.derive_posteriors drives (gpmodelling.py:247-264):
+ * EnsembleSampler.sample -> RedBlueMove (two random halves) -> StretchMove (scale a) -> log-probability of the
+ * half ensemble = GPModelling._log_probability (:127-152) -> accept / reject, for `nsteps` steps and E independent
+ * ensembles in ONE launch (one CTA per ensemble; positions in shared memory).
+ *   S        1: every ensemble samples the same lightcurve; E: ensemble e samples data set e (y, diag [N][S])
+ *   pos      [E][W][ndim] walker positions, updated in place;  lp [E][W] their log-probabilities
+ *   init_lp  non-zero: lp is computed from pos first (start of a run); zero: lp is read (continuation)
+ *   step0    absolute index of the first step (keeps the Philox stream independent of how a run is cut)
+ *   chain    [E][nsteps][W][ndim] (emcee's (steps, walkers, ndim) per ensemble), chain_lp [E][nsteps][W]; may be NULL
+ *   n_accept [E][W] accepted moves, ACCUMULATED; may be NULL
+ *   best_lp  [E] largest log-probability any walker of the ensemble visited during the run (what the reference's LRT
+ *            keeps: GPModelling.max_loglikelihood, gpmodelling.py:405-410), best_pos [E][ndim] where; may be NULL
+ * The box prior is always applied (outside: log-probability -inf, as _log_probability).            */
+int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, int W,
+                     const double *t, const double *y, const double *diag, const double *ds_mean,
+                     double *pos, double *lp, int init_lp, int nsteps, double a, uint64_t seed, uint64_t step0,
+                     double *chain, double *chain_lp, int32_t *n_accept, double *best_lp, double *best_pos,
+                     uint32_t flags, void *stream);
+/* host buffers; here y, diag are [S][N] (one lightcurve per row) */
+int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
+                      const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
+                      double *pos, double *lp, int init_lp, int nsteps, double a, uint64_t seed, uint64_t step0,
+                      double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags);
+
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers for the *_host entry points (cudaMallocHost / cudaFreeHost). */
 int mtg_host_alloc(void **ptr, uint64_t bytes);

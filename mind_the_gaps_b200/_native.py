@@ -106,6 +106,12 @@ SIGNATURES = {
     "mtg_prepare_data_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mtg_group_best_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "mtg_predict_host": (ctypes.c_int, [_mp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mtg_ensemble_dev": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                        _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),
+    "mtg_ensemble_host": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                         _vp, _vp, _vp, ctypes.c_uint32]),
     "mtg_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "mtg_host_free": (ctypes.c_int, [_vp]),
     "mtg_test_math_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),

@@ -11,23 +11,8 @@
 // K6 (Emmanoulopoulos PDF adjustment) lives in mtg_e13.cu.
 #include "mtg_sim.cuh"
 
-// ---- Philox4x32-10 (Salmon et al. 2011) -----------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-__device__ __forceinline__ double u01_from_bits(uint32_t a, uint32_t b)      // (0, 1), 53 bits
-{
-    const uint64_t v = (((uint64_t)a << 32) | b) >> 11;
-    return ((double)v + 0.5) * 1.1102230246251565e-16;
-}
+#include "mtg_philox.cuh"
+
 // two uniforms for (stream `purpose`, item, draw)
 __device__ __forceinline__ double2 philox_u2(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
 {

@@ -7,8 +7,9 @@ class.  What changed underneath:
 * ``self.gp`` is ``mind_the_gaps_b200.celerite.GP`` (K1/K2 kernels) instead of ``celerite.GP``;
 * ``fit`` runs the batched device L-BFGS with analytic gradients (one problem here; the LRT driver
   hands it thousands) and returns a ``scipy.optimize.OptimizeResult`` like ``scipy.optimize.minimize``;
-* ``derive_posteriors`` evaluates each half-ensemble of the stretch move in ONE kernel launch
-  (``vectorize=True`` seam of emcee) -- ``cores`` is accepted and ignored, there is no process pool;
+* ``derive_posteriors`` runs emcee's stretch-move loop inside ONE kernel launch per convergence interval
+  (``sampler.DeviceEnsembleSampler``, kernel K8; ``device_sampler=False`` keeps the host loop with one batched K1
+  launch per half step) -- ``cores`` is accepted and ignored, there is no process pool;
 * ``generate_from_posteriors`` simulates all ``nsims`` lightcurves in one batched device call
   (``cpus`` accepted and ignored).
 """
@@ -22,7 +23,7 @@ from .celerite import GP
 from .celerite.modeling import ConstantModel
 from .lightcurves import GappyLightcurve
 from .models import GaussianModel, LinearModel
-from .sampler import EnsembleSampler
+from .sampler import DeviceEnsembleSampler, EnsembleSampler
 
 __all__ = ["GPModelling"]
 
@@ -106,7 +107,7 @@ class GPModelling(object):
 
     # -- posteriors -----------------------------------------------------------------------------------------
     def derive_posteriors(self, initial_chain_params=None, fit=True, converge=True, max_steps=10000,
-                          convergence_steps=500, walkers=12, cores=6, progress=True):
+                          convergence_steps=500, walkers=12, cores=6, progress=True, device_sampler=True):
         if initial_chain_params is None:
             if not fit:
                 initial_params = self.initial_params
@@ -117,7 +118,12 @@ class GPModelling(object):
         old_tau = np.inf
         self.converged = False
         y = self._lightcurve.y
-        sampler = EnsembleSampler(walkers, self._ndim, lambda p: self.gp.log_probability_batch(y, p), vectorize=True)
+        if device_sampler:
+            # the whole stretch-move loop on the GPU (kernel K8), one launch per convergence interval
+            sampler = DeviceEnsembleSampler(walkers, self.gp, y, block=every_samples)
+        else:
+            # host loop, one batched K1 launch per half step (emcee's vectorize=True seam)
+            sampler = EnsembleSampler(walkers, self._ndim, lambda p: self.gp.log_probability_batch(y, p), vectorize=True)
         tau = None
         for sample in sampler.sample(initial_chain_params, iterations=max_steps, progress=progress):
             if sampler.iteration % every_samples:

@@ -97,7 +97,7 @@ def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
 def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
                      extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
                      max_iter=200, device=None, distributed=None, chunk=None, pipeline=3, return_lightcurves=False,
-                     simulator_kwargs=None):
+                     simulator_kwargs=None, refine_walkers=0, refine_steps=0):
     """Simulate one lightcurve per row of ``null_samples`` (posterior draws of the null kernel's
     parameters) on the window of ``lightcurve`` and MLE-fit each with both kernels.
 
@@ -107,7 +107,13 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     (default: ``ceil(local / pipeline)`` clamped to 2048..8192) and up to ``pipeline`` chunks are in flight at once,
     each on its own CUDA stream with its own simulator workspace: the few slowly converging fits that end every
     batched L-BFGS (a latency-bound tail of ~1 ms rounds) then overlap the FFTs and the bulk of the other chunks'
-    fits instead of idling the GPU.  Returns an ``LRTResult`` holding the arrays for ALL simulations (gathered
+    fits instead of idling the GPU.
+
+    ``refine_walkers, refine_steps``: when both are positive every fit is followed, as in the reference's notebook
+    (``GPModelling(lc, kernel).derive_posteriors(fit=True, walkers=30, max_steps=500)`` then ``max_loglikelihood``,
+    tutorial_ppp.ipynb cells 11-13), by a short stretch-move chain started in a 10 % Gaussian ball around the optimum
+    (``spread_walkers``) -- all simulations in lock step in ONE launch of the device ensemble sampler (kernel K8) --
+    and the largest log-likelihood visited replaces the optimiser's.  Returns an ``LRTResult`` holding the arrays for ALL simulations (gathered
     over ranks when ``torch.distributed`` is initialised)."""
     import concurrent.futures
     import torch
@@ -163,6 +169,25 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     ev = lambda: torch.cuda.Event(enable_timing=True)
     main_stream = torch.cuda.current_stream(device)
 
+    refine = int(refine_walkers) > 0 and int(refine_steps) > 0
+
+    def mcmc_refine(model, nd, lo, hi, x_best, f_best, Lc, y, diag, means, rng, sp, purpose):
+        """max over a short ensemble run around ``x_best`` (Lc, nd); returns (loglike (Lc,), params (Lc, nd))"""
+        W = int(refine_walkers)
+        std = np.abs(x_best) * 0.1
+        p0 = x_best[:, None, :] + rng.normal(size=(Lc, W, nd)) * std[:, None, :]
+        p0[:, 0, :] = x_best                                   # keep the optimum itself in the ensemble
+        p0 = np.clip(p0, lo, hi)
+        pos = torch.from_numpy(np.ascontiguousarray(p0)).to(device)
+        lpw = torch.empty((Lc, W), dtype=torch.float64, device=device)
+        blp = torch.empty(Lc, dtype=torch.float64, device=device); bpos = torch.empty((Lc, nd), dtype=torch.float64, device=device)
+        _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N, Lc, Lc, W, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(), means.data_ptr(),
+                                           pos.data_ptr(), lpw.data_ptr(), 1, int(refine_steps), 2.0, int(seed) * 7919 + purpose, 0,
+                                           None, None, None, blp.data_ptr(), bpos.data_ptr(), _native.FLAG_DS_MEAN, sp))
+        b = blp.cpu().numpy(); bp = bpos.cpu().numpy()
+        better = b > f_best
+        return np.where(better, b, f_best), np.where(better[:, None], bp, x_best)
+
     def worker(slot_chunks):
         """One pipeline slot: its own stream and simulator workspace, chunks processed in order."""
         torch.cuda.set_device(device)
@@ -179,6 +204,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                 for c0 in slot_chunks:
                     Lc = min(chunk, L - c0)
                     rng = np.random.default_rng([int(seed), int(rank), int(c0)])
+                    rng_ref = np.random.default_rng([int(seed), int(rank), int(c0), 99])      # refinement draws: fits stay identical with / without it
                     p_dev = torch.from_numpy(np.ascontiguousarray(mine[c0:c0 + Lc])).to(device)
                     rates = torch.empty((N, Lc), dtype=torch.float64, device=device)
                     y = torch.empty_like(rates); dy = torch.empty_like(rates); diag = torch.empty_like(rates)
@@ -202,9 +228,12 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                                                     oi.data_ptr(), os_.data_ptr(), _native.FLAG_DS_MEAN, sp))
                     best0 = torch.empty(Lc, dtype=torch.float64, device=device); arg0 = torch.empty(Lc, dtype=torch.int32, device=device)
                     _native.check(lib.mtg_group_best_dev(Lc, n_starts_null, of.data_ptr(), best0.data_ptr(), arg0.data_ptr(), sp))
-                    e2.record(stream)
                     a0 = arg0.cpu().numpy().astype(np.int64)
                     x_null = ox.cpu().numpy()[a0]
+                    ll_null = -best0.cpu().numpy()
+                    if refine:
+                        ll_null, x_null = mcmc_refine(m0, nd0, lo0, hi0, x_null, ll_null, Lc, y, diag, means, rng_ref, sp, 1)
+                    e2.record(stream)
                     # ---- alternative fits ---------------------------------------------------------------------------
                     x1 = alternative_starts(x_alt0, x_null, null_slots, lo1, hi1, n_starts_alt, rng).reshape(Lc * n_starts_alt, nd1)
                     B1 = Lc * n_starts_alt
@@ -216,13 +245,17 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                                                     ai.data_ptr(), as_.data_ptr(), _native.FLAG_DS_MEAN, sp))
                     best1 = torch.empty(Lc, dtype=torch.float64, device=device); arg1 = torch.empty(Lc, dtype=torch.int32, device=device)
                     _native.check(lib.mtg_group_best_dev(Lc, n_starts_alt, af.data_ptr(), best1.data_ptr(), arg1.data_ptr(), sp))
+                    a1 = arg1.cpu().numpy().astype(np.int64)
+                    x_alt = ax.cpu().numpy()[a1]
+                    ll_alt = -best1.cpu().numpy()
+                    if refine:
+                        ll_alt, x_alt = mcmc_refine(m1, nd1, lo1, hi1, x_alt, ll_alt, Lc, y, diag, means, rng_ref, sp, 2)
                     e3.record(stream)
                     stream.synchronize()
                     local["simulate_ms"] += e0.elapsed_time(e1); local["fit_null_ms"] += e1.elapsed_time(e2); local["fit_alt_ms"] += e2.elapsed_time(e3)
-                    a1 = arg1.cpu().numpy().astype(np.int64)
                     sl = slice(c0, c0 + Lc)
-                    out_l0[sl] = -best0.cpu().numpy(); out_l1[sl] = -best1.cpu().numpy()
-                    out_p0[sl] = x_null; out_p1[sl] = ax.cpu().numpy()[a1]
+                    out_l0[sl] = ll_null; out_l1[sl] = ll_alt
+                    out_p0[sl] = x_null; out_p1[sl] = x_alt
                     out_s0[sl] = os_.cpu().numpy()[a0]; out_s1[sl] = as_.cpu().numpy()[a1]
                     if return_lightcurves:
                         kept[c0] = (y.cpu().numpy().T.copy(), dy.cpu().numpy().T.copy())

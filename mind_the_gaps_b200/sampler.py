@@ -10,9 +10,13 @@ and the whole half is handed to the log-probability function in ONE call -- with
 emcee is not importable in this environment; this is a restatement of its published algorithm, not
 a copy, and the random stream differs (NumPy ``Generator`` instead of emcee's ``RandomState``).
 """
+import ctypes
+
 import numpy as np
 
-__all__ = ["EnsembleSampler", "integrated_time", "AutocorrError"]
+from . import _native
+
+__all__ = ["EnsembleSampler", "DeviceEnsembleSampler", "integrated_time", "AutocorrError"]
 
 
 class AutocorrError(Exception):
@@ -159,3 +163,119 @@ class EnsembleSampler(object):
     @property
     def acceptance_fraction(self):
         return self._accepted / max(self.iteration, 1)
+
+
+class DeviceEnsembleSampler(EnsembleSampler):
+    """The same sampler with the whole loop on the GPU (kernel K8, ``csrc/mtg_ensemble.cu``): proposals, the celerite
+    log-probability, acceptance and chain storage run inside one kernel launch per block of steps, for ``E``
+    independent ensembles in lock step.
+
+    ``gp``: a computed ``mind_the_gaps_b200.celerite.GP`` (its kernel / mean / bounds define the log-probability,
+    i.e. ``GPModelling._log_probability``); ``y``: ``(N,)`` one lightcurve shared by every ensemble, or ``(E, N)`` one
+    per ensemble with ``yerr`` ``(E, N)`` (the simulated lightcurves of the LRT).  With ``E == 1`` the emcee-shaped
+    results (``get_chain`` -> ``(steps, walkers, ndim)``) are unchanged; with ``E > 1`` they gain a leading
+    ensemble axis.  ``block``: steps per kernel launch of ``sample`` (the generator yields once per block, with
+    ``iteration`` advanced by the block; ``GPModelling.derive_posteriors`` sets it to its convergence interval)."""
+
+    def __init__(self, nwalkers, gp, y, yerr=None, ensembles=1, a=2.0, seed=None, block=100, frozen_mean=None):
+        model = gp.device_model()
+        ndim = int(model.n_free)
+        if nwalkers < 2 * ndim:
+            raise ValueError("the number of walkers must be at least twice the dimension (got %d for ndim=%d)" % (nwalkers, ndim))
+        _native.require_device()
+        self.nwalkers, self.ndim = int(nwalkers), ndim
+        self.a = float(a)
+        self.block = max(1, int(block))
+        self._model = model
+        self._t = np.ascontiguousarray(gp._t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            self._y = y[None, :]
+            self._diag = np.ascontiguousarray(gp._diag, dtype=np.float64)[None, :]
+            self.E = int(ensembles)
+        else:
+            if yerr is None:
+                raise ValueError("per-ensemble lightcurves need their own yerr (E, N)")
+            self._y = y
+            self._diag = np.ascontiguousarray((np.asarray(yerr, dtype=np.float64) + 0.0) ** 2)
+            self.E = y.shape[0]
+            if ensembles not in (1, self.E):
+                raise ValueError("ensembles must equal the number of lightcurves")
+        if self._y.shape[1] != len(self._t) or self._diag.shape != self._y.shape:
+            raise ValueError("dimension mismatch")
+        self._means = None
+        self._flags = 0
+        if frozen_mean is not None:
+            self._means = np.ascontiguousarray(np.broadcast_to(np.asarray(frozen_mean, dtype=np.float64), (self._y.shape[0],)))
+            self._flags = _native.FLAG_DS_MEAN
+        self._seed = int(seed if seed is not None else np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + \
+            int(np.random.randint(0, 2 ** 31 - 1))
+        self.reset()
+
+    def reset(self):
+        self.iteration = 0
+        shape = (self.E,) if self.E > 1 else ()
+        self._chain = np.empty(shape + (0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty(shape + (0, self.nwalkers))
+        self._accepted_i = np.zeros((self.E, self.nwalkers), dtype=np.int32)
+
+    def _run(self, pos, lp, init, nsteps, store):
+        E, W, nd = self.E, self.nwalkers, self.ndim
+        chain = np.empty((E, nsteps, W, nd)) if store else None
+        clp = np.empty((E, nsteps, W)) if store else None
+        rc = _native.lib().mtg_ensemble_host(ctypes.byref(self._model), len(self._t), self._y.shape[0], E, W, _native.ptr(self._t),
+                                             _native.ptr(self._y), _native.ptr(self._diag), _native.ptr(self._means),
+                                             _native.ptr(pos), _native.ptr(lp), int(init), int(nsteps), self.a, self._seed,
+                                             int(self.iteration), _native.ptr(chain), _native.ptr(clp),
+                                             _native.ptr(self._accepted_i), self._flags)
+        _native.check(rc)
+        return chain, clp
+
+    def sample(self, initial_state, iterations=1, progress=False, store=True):
+        E, W, nd = self.E, self.nwalkers, self.ndim
+        p = np.array(initial_state, dtype=np.float64)
+        if p.shape == (W, nd):
+            p = np.repeat(p[None], E, axis=0) if E > 1 else p[None]
+        if p.shape != (E, W, nd):
+            raise ValueError("incompatible input dimensions %r" % (p.shape,))
+        if np.any(~np.isfinite(p)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        for e in range(E if E <= 8 else 1):
+            if W > 1 and np.linalg.cond(np.atleast_2d(np.cov(p[e], rowvar=False))) > 1e8:
+                raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent "
+                                 "for the best performance")
+        p = np.ascontiguousarray(p)
+        lp = np.zeros((E, W))
+        init = True
+        done = 0
+        iterations = int(iterations)
+        while done < iterations:
+            n = min(self.block, iterations - done)
+            chain, clp = self._run(p, lp, init, n, store)
+            init = False
+            if store:
+                ax = 1 if E > 1 else 0
+                self._chain = np.concatenate([self._chain, chain if E > 1 else chain[0]], axis=ax)
+                self._log_prob = np.concatenate([self._log_prob, clp if E > 1 else clp[0]], axis=ax)
+            self.iteration += n
+            done += n
+            yield (p if E > 1 else p[0]), (lp if E > 1 else lp[0])
+
+    def _get(self, arr, discard, thin, flat):
+        if self.E == 1:
+            return super()._get(arr, discard, thin, flat)
+        v = arr[:, : self.iteration][:, discard + thin - 1:: thin]
+        if flat:
+            return v.reshape((v.shape[0], -1) + v.shape[3:])
+        return v
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        if self.E == 1:
+            return super().get_autocorr_time(discard=discard, thin=thin, **kwargs)
+        ch = self.get_chain(discard=discard, thin=thin)
+        return np.array([thin * integrated_time(ch[e], **kwargs) for e in range(self.E)])
+
+    @property
+    def acceptance_fraction(self):
+        f = self._accepted_i / max(self.iteration, 1)
+        return f if self.E > 1 else f[0]

@@ -100,3 +100,28 @@ def test_lrt_driver_null_distribution():
     # same seed -> same simulations and same statistics
     res2 = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, n_starts_null=2, n_starts_alt=6, seed=11)
     np.testing.assert_allclose(res2.loglike_null, res.loglike_null, rtol=1e-12)
+
+
+def test_lrt_with_reference_style_mcmc_refinement():
+    """tutorial_ppp.ipynb cells 11-13: each fit followed by a short ensemble run whose best log-likelihood is kept"""
+    lc, truth = make_lc(200, 4)
+    b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    null_kernel = DampedRandomWalk(truth[0], truth[1], bounds=b_drw)
+    alt_kernel = Lorentzian(truth[0] - 2, np.log(20.0), np.log(2 * np.pi / (10 * DAY)),
+                            bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + \
+        DampedRandomWalk(truth[0], truth[1], bounds=b_drw)
+    samples = truth[None, :] + np.random.default_rng(5).normal(0, 0.15, (40, 2))
+    kw = dict(n_starts_null=2, n_starts_alt=6, seed=11, return_lightcurves=True)
+    plain = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, **kw)
+    ref = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, refine_walkers=30, refine_steps=60, **kw)
+    # same simulations; the refined likelihoods can only improve on the optimiser's
+    np.testing.assert_array_equal(ref.lightcurves[0], plain.lightcurves[0])
+    assert np.all(ref.loglike_null >= plain.loglike_null - 1e-9)
+    # (the alternative's nested start moves with the refined null optimum, so its fits are not identical run to run)
+    assert np.mean(ref.loglike_alt - plain.loglike_alt) > -0.05 and np.mean(ref.loglike_alt >= plain.loglike_alt - 1e-3) > 0.8
+    Y, DY = ref.lightcurves
+    for i in (0, 13, 39):
+        l0 = ogp.loglike_params([("drw",)], ref.params_null[i][None, :], lc.times, Y[i], DY[i])[0]
+        l1 = ogp.loglike_params([("lorentzian",), ("drw",)], ref.params_alt[i][None, :], lc.times, Y[i], DY[i])[0]
+        assert abs(l0 - ref.loglike_null[i]) < 1e-9 * abs(l0) and abs(l1 - ref.loglike_alt[i]) < 1e-9 * abs(l1)
+    assert np.all(np.isfinite(ref.T)) and abs(np.median(ref.T) - np.median(plain.T)) < 3.0
