@@ -198,8 +198,24 @@ def lrt_measurement(torch, rank, world, n_sims):
         runs[mode] = {"wall_s": wall, "sims_per_s": n_sims / wall,
                       "rank0_stage_ms": {k: v for k, v in res.timings.items() if k != "note"},
                       "n_fft": int(lc.get_simulator(null_k.get_psd, extension_factor=2, fft_length=mode).fftndatapoints)}
+    # the reference's own per-simulation procedure: L-BFGS then 30 walkers x 500 steps of MCMC per model, maximum kept
+    kw = dict(n_starts_null=2, n_starts_alt=8, seed=3, distributed=(world > 1), simulator_kwargs={"fft_length": "exact"},
+              refine_walkers=30, refine_steps=500)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res_r = lrt.simulate_and_fit(lc, null_k, alt_k, samples, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        w = torch.tensor([wall], dtype=torch.float64, device="cuda"); dist.all_reduce(w, op=dist.ReduceOp.MAX); wall = float(w.item())
+    refined = {"wall_s": wall, "sims_per_s": n_sims / wall, "walkers": 30, "steps": 500, "fft_length": "exact",
+               "logprob_evals": int(n_sims) * 2 * 30 * 501, "T_median": float(np.median(res_r.T)), "T_p95": float(np.percentile(res_r.T, 95))}
     return {"sims_total": n_sims, "sims_per_gpu": -(-n_sims // world), "scaling": "strong", "starts": {"null": 2, "alt": 8},
-            "fft_length": runs, "note": "exact = the reference's grid length (a prime here -> Bluestein FFT); fast = opt-in 7-smooth length",
+            "mcmc_refined": refined, "fft_length": runs, "note": "exact = the reference's grid length (a prime here -> Bluestein FFT); fast = opt-in 7-smooth length",
             "wall_s": runs["exact"]["wall_s"], "sims_per_s": runs["exact"]["sims_per_s"],
             "T_median": float(np.median(res.T)), "T_p95": float(np.percentile(res.T, 95)),
             "all_finite": bool(np.all(np.isfinite(res.T))), "n_results": int(len(res.T))}
@@ -362,6 +378,26 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
                                           d_p.data_ptr(), s_ll.data_ptr(), s_st.data_ptr(), _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
     ms = timed(k1_small, 20)
     out["half_ensemble_of_64_walkers"] = {"batch": 32, "ms": ms, "evals_per_s": 32 / (ms * 1e-3)}
+    # ---- the emcee loop of derive_posteriors on the device (kernel K8): one 64-walker ensemble as the reference runs it
+    #      (latency bound: steps/s), and 2368 ensembles in lock step (throughput: log-probability evaluations/s)
+    try:
+        W = WALKERS
+        res = {}
+        for label, E, nsteps in (("one_ensemble_64_walkers", 1, 400), ("2368_ensembles_64_walkers", 2368, 20)):
+            pos = d_p[:E * W].clone().reshape(E, W, 5).contiguous()
+            lpw = torch.empty((E, W), dtype=torch.float64, device=dev)
+            acc = torch.zeros((E, W), dtype=torch.int32, device=dev)
+            def k8():
+                _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N_POINTS, 1, E, W, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
+                                                   pos.data_ptr(), lpw.data_ptr(), 1, nsteps, 2.0, 12345, 0, None, None, acc.data_ptr(), None, None,
+                                                   0, stream.cuda_stream))
+            ms = timed(k8, 2)
+            res[label] = {"ensembles": E, "walkers": W, "steps": nsteps, "ms": ms, "steps_per_s": nsteps / (ms * 1e-3),
+                          "logprob_evals_per_s": E * W * (nsteps + 1) / (ms * 1e-3),
+                          "acceptance": float(acc.double().mean().item()) / (3 * nsteps)}
+        out["ensemble_sampler"] = res
+    except Exception as exc:
+        out["ensemble_sampler"] = {"error": repr(exc)}
     # ---- config C4: the full Protassov LRT, 10^4 simulations (DRW null vs Lorentzian + DRW alternative, N = 1000), sharded
     #      over the ranks (strong scaling: the total is fixed); simulate + fit null + fit alternative per simulation
     try:

@@ -54,10 +54,17 @@ __device__ __forceinline__ double exp2_nonpos(double t)
 // exp(x) for x <= 0 through the same kernel (test hook / occasional use)
 __device__ __forceinline__ double exp_nonpos(double x) { return exp2_nonpos(x * MTG_LOG2E); }
 
-// sin(x), cos(x) for finite x; Cody-Waite three-term reduction below 1e5, libdevice beyond
+// Fast-path limit of the sincos kernels: |x| < 2^40.  The reduction r = x - k s (s = pi/2 or pi/128 split in two
+// doubles) is two FMAs: the first is the exactly rounded x - k s_hi (|r| is small, so its rounding error is
+// 2^-53 |r|), the second adds k s_lo ~ |x| 2^-53; what is neglected is k s 2^-106 ~ |x| 2^-106, i.e. < 1e-19 up to
+// 2^40, and k < 2^48 still sits in the low mantissa bits of k + 1.5 2^52.  (A first version stopped at 1e5 and sent
+// larger phases -- omega0 t_n of a fast QPO on a decade-long baseline in seconds -- to libdevice's Payne-Hanek
+// path, which stalls the whole warp for one lane: the ensemble sampler ran 2.5x slower once walkers got there.)
+#define MTG_TRIG_FAST_LIMIT_HI 0x42700000
+// sin(x), cos(x) for finite x; Cody-Waite reduction below 2^40, libdevice beyond
 __device__ __forceinline__ void sincos_fast(double x, double *sn, double *cs)
 {
-    if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) { sincos(x, sn, cs); return; }      // |x| >= 1e5 (or NaN/inf): libdevice
+    if ((__double2hiint(x) & 0x7fffffff) >= MTG_TRIG_FAST_LIMIT_HI) { sincos(x, sn, cs); return; }      // |x| >= 2^40 (or NaN/inf): libdevice
     const double kd = fma(x, TRIG_K[0], TRIG_K[4]);
     const int q = __double2loint(kd);
     const double kf = kd - TRIG_K[4];
@@ -114,10 +121,10 @@ __device__ __forceinline__ double exp2_nonpos_tab(double t, const Tabs &tb)
     return (unsigned)__double2hiint(t) > 0xC08FE000u ? 0.0 : p;
 }
 
-// sin(x), cos(x) for finite x, absolute error < 2e-16; libdevice beyond |x| = 1e5
+// sin(x), cos(x) for finite x, absolute error < 2e-16; libdevice beyond |x| = 2^40
 __device__ __forceinline__ void sincos_tab(double x, const Tabs &tb, double *sn, double *cs)
 {
-    if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) { sincos(x, sn, cs); return; }
+    if ((__double2hiint(x) & 0x7fffffff) >= MTG_TRIG_FAST_LIMIT_HI) { sincos(x, sn, cs); return; }
     const double kd = fma(x, TRIGT_C[0], TRIG_K[4]);
     const int q = __double2loint(kd) & (MTG_TRIG_TAB_N - 1);
     const double kf = kd - TRIG_K[4];

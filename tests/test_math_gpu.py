@@ -37,7 +37,7 @@ def test_exp2_of_nonpositive_arguments(variant):
 @pytest.mark.parametrize("variant", [0, 1])
 def test_sincos_phase_range(variant):
     rng = np.random.default_rng(1)
-    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 200000), rng.uniform(1e5, 1e9, 1000),
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 200000), rng.uniform(1e5, 1e9, 100000), rng.uniform(1e9, 1.0e12, 100000), rng.uniform(1.2e12, 1e15, 1000),
                         np.arange(-600, 600) * (np.pi / 256),
                         [0.0, np.pi / 4, np.pi / 2, np.pi, 1e-8, -1e-8, 99999.9]])
     _, s, c, _ = run(x, variant)
