@@ -1,6 +1,7 @@
 // mtg_capi.cu -- C-ABI glue: model compilation, error reporting, host-buffer entry points,
 // measurement probes.  See include/mtg_b200.h for the contract of every symbol.
 #include "mtg_common.cuh"
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -147,13 +148,20 @@ struct DevBuf {
 };
 struct HostCtx {
     std::mutex mu; cudaStream_t stream = nullptr; int device = -1;
+    static constexpr int NPIPE = 3;
+    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};      // chunk pipeline of large host calls
+    cudaEvent_t data_ready = nullptr;
     DevBuf t, y, d, ysn, dsn, mean, par, ll, grad, st, x, nll, it, scratch;
     int ensure()
     {
         int dev = 0;
         MTG_CUDA(cudaGetDevice(&dev));
         if (stream && dev == device) return 0;
-        if (!stream) MTG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!stream) {
+            MTG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            for (int i = 0; i < NPIPE; ++i) MTG_CUDA(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
+            MTG_CUDA(cudaEventCreateWithFlags(&data_ready, cudaEventDisableTiming));
+        }
         device = dev; return 0;
     }
 };
@@ -233,20 +241,49 @@ static int host_eval(const mtg_model_t *model, int N, int S, int group, int B,
     if ((rc = c.par.reserve(sizeof(double) * (size_t)B * (nd > 0 ? nd : 1))) || (rc = c.ll.reserve(sizeof(double) * B)) ||
         (rc = c.st.reserve(sizeof(int32_t) * B))) return rc;
     if (out_grad && (rc = c.grad.reserve(sizeof(double) * (size_t)B * (nd > 0 ? nd : 1)))) return rc;
-    if (nd > 0) MTG_CUDA(cudaMemcpyAsync(c.par.p, params, sizeof(double) * (size_t)B * nd, cudaMemcpyHostToDevice, c.stream));
-    if (out_grad)
-        rc = mtg_loglike_grad_dev(model, N, S, group, B, (const double *)c.t.p, (const double *)c.y.p, (const double *)c.d.p,
-                                  (const double *)c.mean.p, (const double *)c.par.p, (double *)c.ll.p, (double *)c.grad.p,
-                                  (int32_t *)c.st.p, flags, c.stream);
-    else
-        rc = mtg_loglike_dev(model, N, S, group, B, (const double *)c.t.p, (const double *)c.y.p, (const double *)c.d.p,
-                             (const double *)c.mean.p, (const double *)c.par.p, (double *)c.ll.p, (int32_t *)c.st.p, flags, c.stream);
-    if (rc) return rc;
-    MTG_CUDA(cudaMemcpyAsync(out_ll, c.ll.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c.stream));
-    if (out_grad && nd > 0) MTG_CUDA(cudaMemcpyAsync(out_grad, c.grad.p, sizeof(double) * (size_t)B * nd, cudaMemcpyDeviceToHost, c.stream));
-    if (status) MTG_CUDA(cudaMemcpyAsync(status, c.st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, c.stream));
-    MTG_CUDA(cudaStreamSynchronize(c.stream));
-    return 0;
+    // One chunk = H2D of its parameter rows, the kernel, D2H of its results, all on one stream.  Large batches are cut
+    // into chunks of whole data-set groups (about two full waves of K1) that rotate over NPIPE streams, so the copy
+    // engines run under the kernels of the neighbouring chunks instead of in front of / behind one big launch.
+    auto run_chunk = [&](size_t b0, int Bc, cudaStream_t s) -> int {
+        const size_t ds0 = b0 / (size_t)group;
+        const double *yd = (const double *)c.y.p + ds0, *dd = (const double *)c.d.p + ds0;
+        const double *md = (flags & MTG_FLAG_DS_MEAN) ? (const double *)c.mean.p + ds0 : (const double *)c.mean.p;
+        double *pd = (double *)c.par.p + b0 * (size_t)(nd > 0 ? nd : 1), *ld = (double *)c.ll.p + b0;
+        int32_t *sd = (int32_t *)c.st.p + b0;
+        if (nd > 0) MTG_CUDA(cudaMemcpyAsync(pd, params + b0 * (size_t)nd, sizeof(double) * (size_t)Bc * nd, cudaMemcpyHostToDevice, s));
+        int r;
+        if (out_grad) {
+            double *gd = (double *)c.grad.p + b0 * (size_t)(nd > 0 ? nd : 1);
+            r = mtg_loglike_grad_dev(model, N, S, group, Bc, (const double *)c.t.p, yd, dd, md, pd, ld, gd, sd, flags, s);
+            if (r) return r;
+            if (nd > 0) MTG_CUDA(cudaMemcpyAsync(out_grad + b0 * (size_t)nd, gd, sizeof(double) * (size_t)Bc * nd, cudaMemcpyDeviceToHost, s));
+        } else {
+            r = mtg_loglike_dev(model, N, S, group, Bc, (const double *)c.t.p, yd, dd, md, pd, ld, sd, flags, s);
+            if (r) return r;
+        }
+        MTG_CUDA(cudaMemcpyAsync(out_ll + b0, ld, sizeof(double) * (size_t)Bc, cudaMemcpyDeviceToHost, s));
+        if (status) MTG_CUDA(cudaMemcpyAsync(status + b0, sd, sizeof(int32_t) * (size_t)Bc, cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    const size_t wave2 = 2 * 148 * 512;                               // two K1 waves of 148 SMs x 4 CTAs x 128 threads
+    size_t chunk = ((wave2 + group - 1) / group) * (size_t)group;
+    if ((size_t)B < 2 * chunk) {
+        if ((rc = run_chunk(0, B, c.stream))) return rc;
+        MTG_CUDA(cudaStreamSynchronize(c.stream));
+        return 0;
+    }
+    MTG_CUDA(cudaEventRecord(c.data_ready, c.stream));
+    for (int i = 0; i < HostCtx::NPIPE; ++i) MTG_CUDA(cudaStreamWaitEvent(c.pipe[i], c.data_ready, 0));
+    int k = 0;
+    for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk, ++k) {
+        const int Bc = (int)std::min(chunk, (size_t)B - b0);
+        if ((rc = run_chunk(b0, Bc, c.pipe[k % HostCtx::NPIPE]))) break;
+    }
+    for (int i = 0; i < HostCtx::NPIPE; ++i) {
+        cudaError_t e = cudaStreamSynchronize(c.pipe[i]);
+        if (e != cudaSuccess && !rc) rc = mtg_cuda_check(e, "pipeline sync");
+    }
+    return rc;
 }
 
 extern "C" int mtg_loglike_host(const mtg_model_t *model, int N, int S, int group, int B,

@@ -183,3 +183,54 @@ def test_large_batch_linearity_property():
     # and a sample of the big batch against the oracle
     idx = np.random.default_rng(4).choice(B, 128, replace=False)
     np.testing.assert_allclose(ll[idx], ogp.loglike_params(spec, p[idx], t, y, dy), rtol=RTOL)
+
+
+@pytest.mark.parametrize("S,group", [(1, 1), (40417, 9)])
+def test_host_call_chunk_pipeline_matches_unpipelined_slices(S, group):
+    """Batches of >= 4 K1 waves go through the host entry's H2D / kernel / D2H chunk pipeline (three streams,
+    chunks of whole data-set groups): results and gradients must equal those of small unpipelined calls
+    and the oracle, with and without per-data-set rates."""
+    N = 24
+    t, _, _, _ = fake_lightcurve(N, 21)
+    rng = np.random.default_rng(S + group)
+    if S == 1:
+        B = 2 * 2 * 148 * 512 + 12345
+        Y = 0.5 + 0.05 * rng.normal(size=(1, N)); DY = rng.uniform(0.01, 0.03, (1, N))
+    else:
+        B = S * group
+        Y = 0.5 + 0.05 * rng.normal(size=(S, N)); DY = rng.uniform(0.01, 0.03, (S, N))
+    kernel, spec = build("drw+lor")
+    model = GP(kernel, mean=0.0).device_model()
+    p = c2_truth()[None, :] + rng.normal(0, 0.1, (B, 5))
+    diag = np.ascontiguousarray((DY + 1e-12) ** 2)
+    means = np.ascontiguousarray(Y.mean(axis=1))
+    tt = np.ascontiguousarray(t)
+    lib = _native.lib()
+
+    def call(sl, ds):
+        Bc = sl.stop - sl.start
+        ll = np.empty(Bc); g = np.empty((Bc, 5)); st = np.empty(Bc, dtype=np.int32)
+        Yc = np.ascontiguousarray(Y[ds]); dc = np.ascontiguousarray(diag[ds]); mc = np.ascontiguousarray(means[ds])
+        pc = np.ascontiguousarray(p[sl])
+        _native.check(lib.mtg_loglike_host(ctypes.byref(model), N, Yc.shape[0], group, Bc, _native.ptr(tt), _native.ptr(Yc), _native.ptr(dc),
+                                           _native.ptr(mc), _native.ptr(pc), _native.ptr(ll), _native.ptr(st), _native.FLAG_DS_MEAN))
+        ll2 = np.empty(Bc)
+        _native.check(lib.mtg_loglike_grad_host(ctypes.byref(model), N, Yc.shape[0], group, Bc, _native.ptr(tt), _native.ptr(Yc), _native.ptr(dc),
+                                                _native.ptr(mc), _native.ptr(pc), _native.ptr(ll2), _native.ptr(g), _native.ptr(st),
+                                                _native.FLAG_DS_MEAN))
+        np.testing.assert_allclose(ll2, ll, rtol=1e-12)
+        return ll, g, st
+
+    ll, g, st = call(slice(0, B), slice(0, S))                      # pipelined
+    assert np.all(st == 0) and np.all(np.isfinite(ll)) and np.all(np.isfinite(g))
+    # the same series through small calls that stay below the pipeline threshold: first, middle (across a chunk seam), last
+    chunk = -(-2 * 148 * 512 // group) * group
+    for b0 in (0, chunk - 5 * group, B - 7 * group):
+        sl = slice(b0, b0 + 7 * group)
+        ds = slice(b0 // group, b0 // group + 7) if S > 1 else slice(0, 1)
+        ll_s, g_s, _ = call(sl, ds)
+        np.testing.assert_array_equal(ll[sl], ll_s)
+        np.testing.assert_array_equal(g[sl], g_s)
+    idx = rng.choice(B, 64, replace=False)
+    ref = np.array([ogp.loglike_params(spec, p[i:i + 1], t, Y[i // group if S > 1 else 0], DY[i // group if S > 1 else 0])[0] for i in idx])
+    np.testing.assert_allclose(ll[idx], ref, rtol=RTOL)
