@@ -515,7 +515,7 @@ def main():
         gp.log_likelihood_batch(y, h_p, apply_prior=True, out=h_ll)
     e2e_s = time.perf_counter() - t0
     h2d = B * 5 * 8 + 3 * N_POINTS * 8
-    d2h = B * 8 + B * 4
+    d2h = B * 8                      # log-likelihoods (status words stay on the device unless asked for)
 
     # ---- secondary measurements (outside the timed region of the headline metric) ----------------
     extras = {}

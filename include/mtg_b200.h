@@ -192,6 +192,10 @@ typedef struct mtg_sim_config {
 
 int mtg_sim_create(const mtg_sim_config_t *cfg, void **sim);
 int mtg_sim_destroy(void *sim);
+/* Destroyed simulators park their chunk buffers and cuFFT plans (gigabytes; Bluestein plans for the reference's
+ * un-padded grid lengths) for the next simulator of the same FFT length on the same device; at most MTG_SIM_POOL
+ * (environment, default 4, 0 disables) workspaces are kept.  mtg_sim_trim releases them. */
+int mtg_sim_trim(void);
 
 /* Generate L noiseless binned lightcurves.
  * PSD source: `model` + params[L][n_free] (celerite kernel PSD evaluated on the device, the

@@ -153,11 +153,13 @@ class GP(ModelSet):
         _native.require_device()
         model = self.device_model()
         ll = out if out is not None else np.empty(B, dtype=np.float64)
-        status = np.empty(B, dtype=np.int32)
+        # the status array is only copied back when asked for: a device->host copy into pageable memory blocks the
+        # calling thread, which would serialise the chunk pipeline of large host calls (csrc/mtg_capi.cu host_eval)
+        status = np.empty(B, dtype=np.int32) if return_status else None
         flags = _native.FLAG_APPLY_PRIOR if apply_prior else 0
         rc = _native.lib().mtg_loglike_host(ctypes.byref(model), len(self._t), 1, max(B, 1), B,
                                             _native.ptr(self._t), _native.ptr(y), _native.ptr(self._diag), None,
-                                            _native.ptr(p), _native.ptr(ll), _native.ptr(status), flags)
+                                            _native.ptr(p), _native.ptr(ll), _native.ptr(status) if return_status else None, flags)
         _native.check(rc)
         return (ll, status) if return_status else ll
 

@@ -266,7 +266,8 @@ static int host_eval(const mtg_model_t *model, int N, int S, int group, int B,
         return 0;
     };
     const size_t wave2 = 2 * 148 * 512;                               // two K1 waves of 148 SMs x 4 CTAs x 128 threads
-    size_t chunk = ((wave2 + group - 1) / group) * (size_t)group;
+    // one shared data set (S == 1, group >= B): any cut is a whole-group cut, every chunk reads data set 0
+    size_t chunk = (S == 1) ? wave2 : ((wave2 + group - 1) / group) * (size_t)group;
     if ((size_t)B < 2 * chunk) {
         if ((rc = run_chunk(0, B, c.stream))) return rc;
         MTG_CUDA(cudaStreamSynchronize(c.stream));
@@ -397,12 +398,16 @@ __global__ void k_test_math(int n, int variant, const double *__restrict__ x, do
                             double *__restrict__ c, double *__restrict__ rc)
 {
     __shared__ alignas(16) double tabs_sm[MTG_TABS_DOUBLES];
+    extern __shared__ double2 big_sm[];                    // MTG_TABSB_DOUBLES doubles when variant == 2
     const mtgm::Tabs tb = mtgm::tabs_fill(tabs_sm);
+    mtgm::TabsBig tbb{nullptr, nullptr};
+    if (variant == 2) tbb = mtgm::tabs_fill_big(reinterpret_cast<double *>(big_sm));
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double sn, cs;
     if (variant == 0) { e[i] = mtgm::exp2_nonpos(x[i]); mtgm::sincos_fast(x[i], &sn, &cs); }
+    else if (variant == 2) { e[i] = mtgm::exp2_nonpos_tab(x[i], tbb); mtgm::sincos_tab(x[i], tbb, &sn, &cs); }
     else { e[i] = mtgm::exp2_nonpos_tab(x[i], tb); mtgm::sincos_tab(x[i], tb, &sn, &cs); }
     s[i] = sn; c[i] = cs;
     rc[i] = mtgm::rcp_pos(fabs(x[i]));
@@ -415,7 +420,9 @@ extern "C" int mtg_test_math_host(int n, int variant, const double *x, double *o
     const size_t m = (size_t)n;
     MTG_CUDA(cudaMalloc((void **)&d, sizeof(double) * 5 * m));
     MTG_CUDA(cudaMemcpy(d, x, sizeof(double) * m, cudaMemcpyHostToDevice));
-    k_test_math<<<(n + 255) / 256, 256>>>(n, variant, d, d + m, d + 2 * m, d + 3 * m, d + 4 * m);
+    const size_t dyn = variant == 2 ? sizeof(double) * MTG_TABSB_DOUBLES : 0;
+    if (dyn) MTG_CUDA(cudaFuncSetAttribute(k_test_math, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_test_math<<<(n + 255) / 256, 256, dyn>>>(n, variant, d, d + m, d + 2 * m, d + 3 * m, d + 4 * m);
     mtg_count_launch();
     int rc = mtg_cuda_check(cudaMemcpy(out_exp, d + m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");
     if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_sin, d + 2 * m, sizeof(double) * m, cudaMemcpyDeviceToHost), "d2h");

@@ -14,29 +14,36 @@
 // next step's values are prefetched one step ahead.
 #include "mtg_recursion.cuh"
 
-#ifndef K1_THREADS
-#define K1_THREADS 128
+// CTA shape per recursion width J = JR + 2 JC.  Every CTA carries 48 KB of lookup tables + <= 12 KB of tiles, so at
+// most 3 CTAs fit the 227 KB of an SM: the narrow recursions (J <= 3, <= 128 registers) run 256 threads x 2 CTAs
+// (16 warps per SM, as 4 x 128 before the tables grew), the wide ones keep 128 threads and their natural
+// register count (J = 7 needs 255).
+#ifndef K1_NARROW_J
+#define K1_NARROW_J 3
 #endif
-#ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 1
-#endif
+constexpr int k1_threads(int J) { return J <= K1_NARROW_J ? 256 : 128; }
+constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? 2 : 1; }
 #ifndef K1_UNROLL
 #define K1_UNROLL 2
 #endif
+// (A hand-rotated software pipeline -- phi / u / v of step i + 1 computed beside the state update of step i through
+//  K1State::prepare / advance -- was measured and dropped: 1.36e8 vs 1.57e8 evaluations/s; the extra live registers
+//  cost more than the filled dependency bubbles gain at the 128-register cap.)
 #define K1_STR2(x) #x
 #define K1_STR(x) K1_STR2(x)
 #define K1_TILE 256
 
 // SHARED: S == 1, rates/variances staged through smem with the times.
 template <int JR, int JC, bool DUAL, bool SHARED>
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
+__global__ void __launch_bounds__(k1_threads(JR + 2 * JC), k1_min_blocks(JR + 2 * JC))
 k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
 {
+    constexpr int K1_THREADS = k1_threads(JR + 2 * JC);
     constexpr int NARR = SHARED ? 3 : 1;
     __shared__ alignas(128) double sm[2][NARR][K1_TILE];
     __shared__ alignas(8) uint64_t bar[2];
-    __shared__ alignas(16) double tabs_sm[MTG_TABS_DOUBLES];
-    const mtgm::Tabs tb = mtgm::tabs_fill(tabs_sm);       // visible after the __syncthreads below
+    extern __shared__ double2 k1_dyn_smem[];                   // MTG_TABSB_DOUBLES doubles: the big lookup tables
+    const mtgm::TabsBig tb = mtgm::tabs_fill_big(reinterpret_cast<double *>(k1_dyn_smem));       // visible after the __syncthreads below
 
     const int tid = threadIdx.x;
     const int b_raw = blockIdx.x * K1_THREADS + tid;
@@ -120,20 +127,34 @@ _Pragma(K1_STR(unroll K1_UNROLL))
 }
 
 // ---- dispatch ---------------------------------------------------------------------------------
+template <int JR, int JC, bool DUAL, bool SHARED>
+static int launch_k1_one(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
+{
+    constexpr size_t dyn = sizeof(double) * MTG_TABSB_DOUBLES;       // 48 KB: above the default limit, opt in once per device
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !opted[dev]) {
+        int rc = mtg_cuda_check(cudaFuncSetAttribute(k1_loglike<JR, JC, DUAL, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn),
+                                "k1_loglike shared-memory opt-in");
+        if (rc) return rc;
+        opted[dev] = true;
+    }
+    constexpr int K1_THREADS = k1_threads(JR + 2 * JC);
+    const dim3 grid((a.B + K1_THREADS - 1) / K1_THREADS), block(K1_THREADS);
+    k1_loglike<JR, JC, DUAL, SHARED><<<grid, block, dyn, stream>>>(pl, a);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k1_loglike launch");
+}
+
 template <int JR, int JC>
 static int launch_k1(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
 {
-    const dim3 grid((a.B + K1_THREADS - 1) / K1_THREADS), block(K1_THREADS);
     const bool shared = (a.S == 1);
-    if (pl.has_sho) {
-        if (shared) k1_loglike<JR, JC, true, true><<<grid, block, 0, stream>>>(pl, a);
-        else        k1_loglike<JR, JC, true, false><<<grid, block, 0, stream>>>(pl, a);
-    } else {
-        if (shared) k1_loglike<JR, JC, false, true><<<grid, block, 0, stream>>>(pl, a);
-        else        k1_loglike<JR, JC, false, false><<<grid, block, 0, stream>>>(pl, a);
-    }
-    mtg_count_launch();
-    return mtg_cuda_check(cudaGetLastError(), "k1_loglike launch");
+    int rc;
+    if (pl.has_sho) rc = shared ? launch_k1_one<JR, JC, true, true>(pl, a, stream) : launch_k1_one<JR, JC, true, false>(pl, a, stream);
+    else            rc = shared ? launch_k1_one<JR, JC, false, true>(pl, a, stream) : launch_k1_one<JR, JC, false, false>(pl, a, stream);
+    return rc;
 }
 
 #define K1_CASE(R, C) if (pl.jr == R && pl.jc == C) return launch_k1<R, C>(pl, a, stream);

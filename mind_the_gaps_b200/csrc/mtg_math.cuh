@@ -138,6 +138,59 @@ __device__ __forceinline__ void sincos_tab(double x, const Tabs &tb, double *sn,
     *cs = fma(CS.x, cm, fma(-CS.y, sr, CS.x));
 }
 
+// ---- big-table variants (K1) --------------------------------------------------------------------------
+// K1 is bound by the FP64 pipe at ~95 % of its issue rate (profiles/r01e_k1_*), so every FP64 instruction removed
+// from the step is throughput.  With 2048-entry tables (48 KB of shared memory per CTA, which K1 can afford and K2 /
+// K8 cannot) the residuals shrink to |r| <= 1/4096 and |r| <= pi/2048:
+//   2^r - 1 = r (c1 + r (c2 + r c3))            truncation (ln2/4096)^4/24 = 3.4e-17     7 FP64 ops (was 8)
+//   sin r   = r - r^3/6, cos r - 1 = -z/2 + z^2/24   truncation 7e-17 / 2e-20           13 FP64 ops (was 15)
+static __constant__ double EXP2B_C[5] = {2048.0, -1.0 / 2048.0, MTG_EXP2_P1, MTG_EXP2_P2, MTG_EXP2_P3};
+// [0] 1024/pi [1] -pi/1024 hi [2] -pi/1024 lo [3] -1/6 [4] -1/2 [5] 1/24
+static __constant__ double TRIGB_C[6] = {MTG_TRIGB_INV_STEP, -MTG_TRIGB_STEP_HI, -MTG_TRIGB_STEP_LO, -1.0 / 6.0, -0.5, 1.0 / 24.0};
+
+#define MTG_TABSB_DOUBLES (MTG_EXP2B_TAB_N + 2 * MTG_TRIGB_TAB_N)
+struct TabsBig { const double *e2; const double *trig; };
+
+__device__ __forceinline__ TabsBig tabs_fill_big(double *smem /* MTG_TABSB_DOUBLES, 16-byte aligned */)
+{
+    for (int i = threadIdx.x; i < MTG_EXP2B_TAB_N; i += blockDim.x) smem[i] = EXP2B_TAB[i];
+    double2 *tr = reinterpret_cast<double2 *>(smem + MTG_EXP2B_TAB_N);
+    const double2 *src = reinterpret_cast<const double2 *>(TRIGB_TAB);
+    for (int i = threadIdx.x; i < MTG_TRIGB_TAB_N; i += blockDim.x) tr[i] = src[i];
+    TabsBig t; t.e2 = smem; t.trig = smem + MTG_EXP2B_TAB_N;
+    return t;
+}
+
+__device__ __forceinline__ double exp2_nonpos_tab(double t, const TabsBig &tb)
+{
+    const double kd = fma(t, EXP2B_C[0], EXP2_K[0]);        // round(2048 t) in the low mantissa bits
+    const int ki = __double2loint(kd);
+    const double r = fma(kd - EXP2_K[0], EXP2B_C[1], t);    // exact, |r| <= 1/4096
+    const double T = tb.e2[ki & (MTG_EXP2B_TAB_N - 1)];
+    double q = fma(r, EXP2B_C[4], EXP2B_C[3]);
+    q = fma(q, r, EXP2B_C[2]);
+    double p = fma(T, q * r, T);
+    const int hi = __double2hiint(p) + ((ki >> 11) << 20);
+    p = __hiloint2double(hi, __double2loint(p));
+    return (unsigned)__double2hiint(t) > 0xC08FE000u ? 0.0 : p;
+}
+
+__device__ __forceinline__ void sincos_tab(double x, const TabsBig &tb, double *sn, double *cs)
+{
+    if ((__double2hiint(x) & 0x7fffffff) >= MTG_TRIG_FAST_LIMIT_HI) { sincos(x, sn, cs); return; }
+    const double kd = fma(x, TRIGB_C[0], TRIG_K[4]);
+    const int q = __double2loint(kd) & (MTG_TRIGB_TAB_N - 1);
+    const double kf = kd - TRIG_K[4];
+    double r = fma(kf, TRIGB_C[1], x);
+    r = fma(kf, TRIGB_C[2], r);                             // |r| <= pi/2048
+    const double2 CS = *reinterpret_cast<const double2 *>(tb.trig + 2 * q);
+    const double z = r * r;
+    const double sr = fma(r * z, TRIGB_C[3], r);                      // sin r
+    const double cm = z * fma(z, TRIGB_C[5], TRIGB_C[4]);             // cos r - 1
+    *sn = fma(CS.y, cm, fma(CS.x, sr, CS.y));
+    *cs = fma(CS.x, cm, fma(-CS.y, sr, CS.x));
+}
+
 // 1/x for a positive normal x: MUFU.RCP64H seed (>= 19 bits) + one cubic Newton step, ~1 ulp.
 // IEEE division costs three more FP64 instructions and a slow-path branch; D <= 0 / denormal / NaN
 // are flagged by the caller independently of this value.

@@ -30,13 +30,16 @@ struct K1State {
         Dp = 0.0; rDp = 0.0; zp = 0.0; tp = t0; chi2 = 0.0; prod = 1.0; esum = 0; bad = false;
     }
 
-    // one observation: (tn, residual rn, diagonal dn).  With the zero-initialised state and
-    // tp = t0 the same code performs the n = 0 start-up (S = 0, f = 0, D = diag + sum a).
-    __device__ __forceinline__ void step(const Coef<JR, JC, DUAL> &c, const mtgm::Tabs &tb, double tn, double rn, double dn, int n)
+    // The per-step quantities that do not depend on the recursion state: phi = exp(-c dt) and the generator rows u, v.
+    // K1 computes them one step AHEAD of the state update (software pipelining): the ~40 FP64 instructions of the
+    // transcendentals then fill the dependency bubbles of the previous step's S -> D -> 1/D -> W chain.
+    struct Pre { double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1]; };
+
+    template <class TB>
+    __device__ __forceinline__ void prepare(const Coef<JR, JC, DUAL> &c, const TB &tb, double tn, double tprev, Pre &q) const
     {
-        const double dt = tn - tp;
-        tp = tn;
-        double p[J > 0 ? J : 1], u[J > 0 ? J : 1], v[J > 0 ? J : 1];
+        const double dt = tn - tprev;
+        double *p = q.p, *u = q.u, *v = q.v;
 #pragma unroll
         for (int j = 0; j < JR; ++j) { p[j] = mtgm::exp2_nonpos_tab(c.ncr[j] * dt, tb); u[j] = c.ar[j]; v[j] = 1.0; }
 #pragma unroll
@@ -58,6 +61,23 @@ struct K1State {
                 v[JR + 2 * j] = 1.0; v[JR + 2 * j + 1] = 1.0;
             }
         }
+    }
+
+    // one observation: (tn, residual rn, diagonal dn).  With the zero-initialised state and
+    // tp = t0 the same code performs the n = 0 start-up (S = 0, f = 0, D = diag + sum a).
+    // TB: mtgm::Tabs (256-entry tables; K2, K8) or mtgm::TabsBig (2048-entry tables; K1)
+    template <class TB>
+    __device__ __forceinline__ void step(const Coef<JR, JC, DUAL> &c, const TB &tb, double tn, double rn, double dn, int n)
+    {
+        Pre q;
+        prepare(c, tb, tn, tp, q);
+        tp = tn;
+        advance(c, q, rn, dn, n);
+    }
+
+    __device__ __forceinline__ void advance(const Coef<JR, JC, DUAL> &c, const Pre &q, double rn, double dn, int n)
+    {
+        const double *p = q.p, *u = q.u, *v = q.v;
         // S <- (phi phi^T) o (S + D W W^T)   [previous D, W];   f <- phi o (f + W z).  With the
         // unnormalised W' = D W:  D W W^T = W' (W'/D)^T and W z = W' (z/D); chi^2 picks up z^2/D here too.
         const double zr = zp * rDp;

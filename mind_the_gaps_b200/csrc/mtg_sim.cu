@@ -10,6 +10,8 @@
 //   K7  k_noise      Poisson / Kraft / Gaussian noise and uncertainties (noise_models.py:49-184)
 // K6 (Emmanoulopoulos PDF adjustment) lives in mtg_e13.cu.
 #include "mtg_sim.cuh"
+#include <mutex>
+#include <vector>
 
 #include "mtg_philox.cuh"
 
@@ -467,14 +469,66 @@ extern "C" int mtg_sim_create(const mtg_sim_config_t *cfg, void **out)
     return 0;
 }
 
+// ---- workspace pool -------------------------------------------------------------------------------
+// A simulator's chunk buffers are gigabytes (n_fft ~ 2.7e6: 43 MB per lightcurve in flight) and its cuFFT plans
+// (Bluestein for the reference's un-padded lengths) take longer to build than a chunk takes to run.  The LRT driver
+// creates one simulator per pipeline slot per call, so destroyed simulators park their buffers and plans here and
+// the next simulator of the same FFT length on the same device adopts them instead of paying cudaMalloc / cudaFree
+// (which synchronises the device) / cufftPlanMany again.  At most MTG_SIM_POOL (default 4) workspaces are kept;
+// mtg_sim_trim() releases them.
+struct SimScratch {
+    int device = -1, n_fft = 0, cap = 0;
+    double2 *d_spec = nullptr; double *d_lc = nullptr; PsdCoef *d_coef = nullptr; SegInfo *d_seg = nullptr;
+    std::map<long long, cufftHandle> plans, plans_d2z;
+};
+static std::mutex g_pool_mu;
+static std::vector<SimScratch> g_pool;
+
+static void scratch_release(SimScratch &w)
+{
+    for (auto &kv : w.plans) cufftDestroy(kv.second);
+    for (auto &kv : w.plans_d2z) cufftDestroy(kv.second);
+    cudaFree(w.d_spec); cudaFree(w.d_lc); cudaFree(w.d_coef); cudaFree(w.d_seg);
+}
+static int pool_limit()
+{
+    if (const char *e = getenv("MTG_SIM_POOL")) return atoi(e);
+    return 4;
+}
+
+extern "C" int mtg_sim_trim(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    int dev = 0; cudaGetDevice(&dev);
+    for (auto &w : g_pool) { cudaSetDevice(w.device); scratch_release(w); }
+    g_pool.clear();
+    cudaSetDevice(dev);
+    return 0;
+}
+
 extern "C" int mtg_sim_destroy(void *p)
 {
     Sim *s = (Sim *)p;
     if (!s) return 0;
-    for (auto &kv : s->plans) cufftDestroy(kv.second);
-    for (auto &kv : s->plans_d2z) cufftDestroy(kv.second);
+    SimScratch w;
+    cudaGetDevice(&w.device);
+    w.n_fft = s->cfg.n_fft; w.cap = s->cap;
+    w.d_spec = s->d_spec; w.d_lc = s->d_lc; w.d_coef = s->d_coef; w.d_seg = s->d_seg;
+    w.plans.swap(s->plans); w.plans_d2z.swap(s->plans_d2z);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    bool parked = false;
+    if (w.cap > 0 && pool_limit() > 0) {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if ((int)g_pool.size() >= pool_limit()) {           // drop the oldest
+            int dev = 0; cudaGetDevice(&dev);
+            cudaSetDevice(g_pool.front().device); scratch_release(g_pool.front()); cudaSetDevice(dev);
+            g_pool.erase(g_pool.begin());
+        }
+        g_pool.push_back(std::move(w));
+        parked = true;
+    }
+    if (!parked) scratch_release(w);
     cudaFree(s->d_grid); cudaFree(s->d_lo); cudaFree(s->d_hi); cudaFree(s->d_exp); cudaFree(s->d_bkg); cudaFree(s->d_err);
-    cudaFree(s->d_spec); cudaFree(s->d_lc); cudaFree(s->d_coef); cudaFree(s->d_seg);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -510,6 +564,18 @@ static int sim_chunk(const Sim *s, int L)
 static int sim_reserve(Sim *s, int chunk)
 {
     if (chunk <= s->cap) return 0;
+    if (s->cap == 0) {          // adopt a parked workspace of the same FFT length that is large enough
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int dev = 0; cudaGetDevice(&dev);
+        for (size_t i = 0; i < g_pool.size(); ++i) {
+            SimScratch &w = g_pool[i];
+            if (w.device != dev || w.n_fft != s->cfg.n_fft || w.cap < chunk) continue;
+            s->d_spec = w.d_spec; s->d_lc = w.d_lc; s->d_coef = w.d_coef; s->d_seg = w.d_seg; s->cap = w.cap;
+            s->plans.swap(w.plans); s->plans_d2z.swap(w.plans_d2z);
+            g_pool.erase(g_pool.begin() + i);
+            return 0;
+        }
+    }
     cudaFree(s->d_spec); cudaFree(s->d_lc); cudaFree(s->d_coef); cudaFree(s->d_seg);
     s->d_spec = nullptr; s->d_lc = nullptr; s->d_coef = nullptr; s->d_seg = nullptr; s->cap = 0;
     int rc;

@@ -1,5 +1,5 @@
 """GPU: the inner loop's own exp / sincos / reciprocal (csrc/mtg_math.cuh) against numpy in extended precision.
-variant 0 = polynomial kernels, variant 1 = the table-driven kernels K1/K2 run."""
+variant 0 = polynomial kernels, variant 1 = the 256-entry table kernels K2/K8 run, variant 2 = the 2048-entry table kernels K1 runs."""
 import numpy as np
 import pytest
 
@@ -21,12 +21,12 @@ def ulps(got, ref):
     return np.abs((got - ref).astype(np.float64)) / np.spacing(np.abs(ref.astype(np.float64)))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_exp2_of_nonpositive_arguments(variant):
     """2^t, t <= 0: the recursion evaluates exp(-c dt) as 2^(-c log2(e) dt) with an exact range reduction."""
     rng = np.random.default_rng(0)
     x = -np.concatenate([rng.uniform(0, 1, 200000), 10.0 ** rng.uniform(-12, 3.0, 200000),
-                         np.arange(0, 2048) / 256.0, np.arange(0, 2048) / 512.0,
+                         np.arange(0, 2048) / 256.0, np.arange(0, 2048) / 512.0, np.arange(0, 8192) / 4096.0,
                          [0.0, 1e-300, 0.5, 1.5, 1000.0, 1019.5]])
     e = run(x, variant)[0]
     assert ulps(e, np.exp2(x.astype(np.longdouble))).max() <= 1.5
@@ -34,11 +34,11 @@ def test_exp2_of_nonpositive_arguments(variant):
     assert np.all(e2 == 0.0)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_sincos_phase_range(variant):
     rng = np.random.default_rng(1)
     x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 200000), rng.uniform(1e5, 1e9, 100000), rng.uniform(1e9, 1.0e12, 100000), rng.uniform(1.2e12, 1e15, 1000),
-                        np.arange(-600, 600) * (np.pi / 256),
+                        np.arange(-600, 600) * (np.pi / 256), np.arange(-5000, 5000) * (np.pi / 2048),
                         [0.0, np.pi / 4, np.pi / 2, np.pi, 1e-8, -1e-8, 99999.9]])
     _, s, c, _ = run(x, variant)
     xl = x.astype(np.longdouble)
