@@ -95,6 +95,8 @@ typedef struct mtg_model {
 /* flags for mtg_loglike_* / mtg_grad_* */
 #define MTG_FLAG_APPLY_PRIOR   1u  /* add celerite log_prior (box, BendingPowerlaw): out = -inf outside  (gpmodelling.py:147-152) */
 #define MTG_FLAG_DS_MEAN       2u  /* residual = y - ds_mean[data set] (mean frozen at mean(y), gpmodelling.py:83-87)            */
+#define MTG_FLAG_SCAN          4u  /* mtg_loglike_*: force the parallel-in-time kernel K9 (MTG_EUNSUP if the model is not covered)  */
+#define MTG_FLAG_NO_SCAN       8u  /* mtg_loglike_*: force the one-thread-per-series kernel K1                                      */
 
 /* ---- library / device ------------------------------------------------------------------ */
 int         mtg_version(void);

@@ -16,6 +16,8 @@ MTG_MAX_PARAMS = 24
 
 FLAG_APPLY_PRIOR = 1
 FLAG_DS_MEAN = 2
+FLAG_SCAN = 4
+FLAG_NO_SCAN = 8
 
 MEAN_CONSTANT, MEAN_LINEAR, MEAN_GAUSSIAN = 0, 1, 2
 

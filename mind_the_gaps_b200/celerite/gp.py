@@ -145,8 +145,13 @@ class GP(ModelSet):
             raise ValueError("expected parameters of shape (B, %d)" % self.vector_size)
         return p
 
-    def log_likelihood_batch(self, y, params, apply_prior=False, return_status=False, out=None):
-        """log-likelihood of ``y`` under B parameter vectors ``params[B, ndim]`` in one launch."""
+    _KERNEL_FLAGS = {"auto": 0, "k1": _native.FLAG_NO_SCAN, "scan": _native.FLAG_SCAN}
+
+    def log_likelihood_batch(self, y, params, apply_prior=False, return_status=False, out=None, kernel="auto"):
+        """log-likelihood of ``y`` under B parameter vectors ``params[B, ndim]`` in one launch.
+
+        ``kernel``: ``"auto"`` (the library picks: the parallel-in-time scan kernel K9 for small batches of narrow
+        kernels, the one-thread-per-series kernel K1 otherwise), ``"k1"`` or ``"scan"`` to force one."""
         y = self._check_y(y)
         p = self._batch_params(params)
         B = p.shape[0]
@@ -156,7 +161,7 @@ class GP(ModelSet):
         # the status array is only copied back when asked for: a device->host copy into pageable memory blocks the
         # calling thread, which would serialise the chunk pipeline of large host calls (csrc/mtg_capi.cu host_eval)
         status = np.empty(B, dtype=np.int32) if return_status else None
-        flags = _native.FLAG_APPLY_PRIOR if apply_prior else 0
+        flags = (_native.FLAG_APPLY_PRIOR if apply_prior else 0) | self._KERNEL_FLAGS[kernel]
         rc = _native.lib().mtg_loglike_host(ctypes.byref(model), len(self._t), 1, max(B, 1), B,
                                             _native.ptr(self._t), _native.ptr(y), _native.ptr(self._diag), None,
                                             _native.ptr(p), _native.ptr(ll), _native.ptr(status) if return_status else None, flags)
@@ -181,10 +186,10 @@ class GP(ModelSet):
         _native.check(rc)
         return (ll, grad, status) if return_status else (ll, grad)
 
-    def log_probability_batch(self, y, params):
+    def log_probability_batch(self, y, params, kernel="auto"):
         """``log_prior + log_likelihood`` for B parameter vectors: ``GPModelling._log_probability``
         (gpmodelling.py:127-152) vectorised; ``-inf`` outside the prior or when not positive definite."""
-        return self.log_likelihood_batch(y, params, apply_prior=True)
+        return self.log_likelihood_batch(y, params, apply_prior=True, kernel=kernel)
 
     # -- celerite single-point API ---------------------------------------------------------------------
     def log_likelihood(self, y, _const=None, quiet=False):

@@ -189,6 +189,8 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // ---- host-side helpers ---------------------------------------------------------------------
 int    mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);
+int    mtg_k9_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);      // parallel-in-time scan (mtg_scan.cu)
+bool   mtg_k9_supports(const Plan &pl);
 size_t mtg_k2_tape_bytes_per_series(const Plan &pl, int N);
 int    mtg_k2_chunk(const Plan &pl, int N, int B);
 // a.B work items (series a.index[i] when a.index != NULL, limited to *a.count when a.count != NULL)

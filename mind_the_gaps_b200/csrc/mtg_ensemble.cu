@@ -18,6 +18,7 @@
 // MT19937 by construction (parity of the sampler is statistical: tests/test_ensemble_gpu.py).
 #include "mtg_recursion.cuh"
 #include "mtg_philox.cuh"
+#include "mtg_ensemble.cuh"
 #include <vector>
 
 #define K8_MAX_THREADS 128          // >= ceil(W/2): at most 256 walkers per ensemble
@@ -28,18 +29,6 @@
 #define K8_INLINE __forceinline__
 #endif
 
-struct EnsembleArgs {
-    int N, S, E, W, nsteps;
-    const double *t, *y, *diag, *ds_mean;
-    double *pos, *lp;                 // [E][W][nd], [E][W]   in / out
-    double *chain, *chain_lp;         // [E][nsteps][W][nd], [E][nsteps][W]   (may be NULL)
-    int32_t *n_accept;                // [E][W] accumulated (may be NULL)
-    double *best_lp, *best_pos;       // [E], [E][nd]: running maximum of the log-probability over the run (may be NULL)
-    double a;                         // stretch scale
-    uint64_t seed, step0;
-    uint32_t flags; int init_lp;
-    int epc;                          // ensembles per CTA (small ensembles share a warp)
-};
 
 // log posterior of one parameter vector on data set `ds` (box prior + celerite log-likelihood).  Deliberately NOT
 // inlined: the recursion loop then gets K1's register allocation (128 registers, 16 warps per SM) instead of sharing
@@ -233,6 +222,12 @@ extern "C" int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, i
     if (W < 2 * pl.n_free) { mtg_set_error("the number of walkers must be at least twice the dimension (got %d for ndim=%d)", W, pl.n_free); return MTG_EINVAL; }
     EnsembleArgs a{N, S, E, W, nsteps, t, y, diag, ds_mean, pos, lp, chain, chain_lp, n_accept, best_lp, best_pos, a_scale, seed, step0, flags, init_lp, 1};
     cudaStream_t stream = (cudaStream_t)stream_;
+    // Few ensembles (derive_posteriors on ONE lightcurve): K8 would run each half ensemble as a 1000-step chain on one
+    // warp.  K10 gives every proposal a whole CTA (parallel-in-time scan, mtg_scan.cu) and separates the half steps by a
+    // per-ensemble barrier across CTAs: same proposals, same random numbers, ~15x the steps per second.
+    const bool can_scan = mtg_k10_fits(pl, N, E, W);
+    if ((flags & MTG_FLAG_SCAN) && !can_scan) { mtg_set_error("MTG_FLAG_SCAN: model / ensemble count not covered by the scan sampler"); return MTG_EUNSUP; }
+    if ((flags & MTG_FLAG_SCAN) || (can_scan && !(flags & MTG_FLAG_NO_SCAN) && N >= 64)) return mtg_k10_dispatch(pl, a, stream);
     K8_CASE(1, 0) K8_CASE(2, 0) K8_CASE(3, 0)
     K8_CASE(0, 1) K8_CASE(1, 1) K8_CASE(2, 1) K8_CASE(3, 1)
     K8_CASE(0, 2) K8_CASE(1, 2) K8_CASE(2, 2)

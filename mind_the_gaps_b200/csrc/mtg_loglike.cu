@@ -13,6 +13,7 @@
 // time-major [N][S] arrays: a warp touches <= 32 consecutive doubles per step (coalesced) and the
 // next step's values are prefetched one step ahead.
 #include "mtg_recursion.cuh"
+#include <cstdlib>
 
 // CTA shape per recursion width J = JR + 2 JC.  Every CTA carries 48 KB of lookup tables + <= 12 KB of tiles, so at
 // most 3 CTAs fit the 227 KB of an SM: the narrow recursions (J <= 3, <= 128 registers) run 256 threads x 2 CTAs
@@ -42,8 +43,10 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
     constexpr int NARR = SHARED ? 3 : 1;
     __shared__ alignas(128) double sm[2][NARR][K1_TILE];
     __shared__ alignas(8) uint64_t bar[2];
-    extern __shared__ double2 k1_dyn_smem[];                   // MTG_TABSB_DOUBLES doubles: the big lookup tables
-    const mtgm::TabsBig tb = mtgm::tabs_fill_big(reinterpret_cast<double *>(k1_dyn_smem));       // visible after the __syncthreads below
+    extern __shared__ __align__(128) double2 k1_dyn_smem[];      // MTG_TABSB_DOUBLES doubles: the big lookup tables
+    __shared__ alignas(8) uint64_t bar_tab;
+    double *tabs_sm = reinterpret_cast<double *>(k1_dyn_smem);
+    mtgm::TabsBig tb; tb.e2 = tabs_sm; tb.trig = tabs_sm + MTG_EXP2B_TAB_N;
 
     const int tid = threadIdx.x;
     const int b_raw = blockIdx.x * K1_THREADS + tid;
@@ -65,9 +68,14 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
             bulk_g2s(&sm[st][2][0], a.diag + (size_t)k * K1_TILE, bytes, &bar[st]);
         }
     };
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar_tab, 1); mbar_fence_init(); }
     __syncthreads();
     if (tid == 0) {
+        // the 48 KB of lookup tables arrive by two TMA bulk copies that overlap the per-series set-up below (a
+        // thread-strided fill cost a latency-bound 32-series call 70 us)
+        mbar_expect_tx(&bar_tab, (uint32_t)(sizeof(double) * MTG_TABSB_DOUBLES));
+        bulk_g2s(tabs_sm, mtgm::EXP2B_TAB, (uint32_t)(sizeof(double) * MTG_EXP2B_TAB_N), &bar_tab);
+        bulk_g2s(tabs_sm + MTG_EXP2B_TAB_N, mtgm::TRIGB_TAB, (uint32_t)(sizeof(double) * 2 * MTG_TRIGB_TAB_N), &bar_tab);
         if (use_bulk(0)) issue(0);
         if (ntiles > 1 && use_bulk(1)) issue(1);
     }
@@ -89,6 +97,7 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
     double y_nx = 0.0, d_nx = 0.0;
     if (!SHARED) { y_nx = __ldg(yp); d_nx = __ldg(dp); }
 
+    mbar_wait(&bar_tab, 0u);                   // tables resident
     uint32_t phase[2] = {0u, 0u};
     for (int k = 0; k < ntiles; ++k) {
         const int st = k & 1, cnt = tile_count(k), n0 = k * K1_TILE;
@@ -170,6 +179,14 @@ int mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
     return MTG_EUNSUP;
 }
 
+// largest batch the automatic dispatch hands to the scan kernel (MTG_SCAN_MAX_B overrides)
+static long long mtg_scan_max_batch()
+{
+    static long long v = -1;
+    if (v < 0) { const char *e = getenv("MTG_SCAN_MAX_B"); v = e ? atoll(e) : 1024; }
+    return v;
+}
+
 extern "C" int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group, int B,
                                const double *t, const double *y, const double *diag, const double *ds_mean,
                                const double *params, double *out_ll, int32_t *status,
@@ -185,5 +202,12 @@ extern "C" int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group
     int rc = mtg_build_plan(model, &pl);
     if (rc) return rc;
     BatchArgs a{N, S, group, B, t, y, diag, ds_mean, params, out_ll, nullptr, status, flags, nullptr, nullptr, nullptr};
+    // Small batches of narrow kernels: one CTA per series, the N-step chain parallelised by a scan (K9, mtg_scan.cu).
+    // K1 needs >= one thread per series to pay off: its latency is that of the whole chain (0.2 ms at N = 1000) whatever
+    // the batch, K9's cost is ~12x the work spread over 256 threads.  Crossover measured at ~2000 series (N = 1000).
+    const bool can_scan = mtg_k9_supports(pl);
+    if ((flags & MTG_FLAG_SCAN) && !can_scan) { mtg_set_error("MTG_FLAG_SCAN: model not covered by the scan kernel"); return MTG_EUNSUP; }
+    const bool scan = (flags & MTG_FLAG_SCAN) || (can_scan && !(flags & MTG_FLAG_NO_SCAN) && N >= 64 && (long long)B * 64 <= mtg_scan_max_batch() * 64LL);
+    if (scan) return mtg_k9_dispatch(pl, a, (cudaStream_t)stream);
     return mtg_k1_dispatch(pl, a, (cudaStream_t)stream);
 }

@@ -166,9 +166,12 @@ class EnsembleSampler(object):
 
 
 class DeviceEnsembleSampler(EnsembleSampler):
-    """The same sampler with the whole loop on the GPU (kernel K8, ``csrc/mtg_ensemble.cu``): proposals, the celerite
-    log-probability, acceptance and chain storage run inside one kernel launch per block of steps, for ``E``
-    independent ensembles in lock step.
+    """The same sampler with the whole loop on the GPU: proposals, the celerite log-probability, acceptance and chain
+    storage run inside one kernel launch per block of steps, for ``E`` independent ensembles in lock step.  Two kernels
+    share the algorithm and the random streams: K8 (``csrc/mtg_ensemble.cu``, one thread per proposal: thousands of
+    ensembles) and K10 (``csrc/mtg_scan.cu``, one CTA per proposal with the parallel-in-time likelihood and a barrier
+    across CTAs per half step: the one-lightcurve case of ``derive_posteriors``); ``kernel="auto"`` lets the library
+    choose (K10 when all ``E * ceil(W/2)`` CTAs fit the device and the model has <= 3 state dimensions).
 
     ``gp``: a computed ``mind_the_gaps_b200.celerite.GP`` (its kernel / mean / bounds define the log-probability,
     i.e. ``GPModelling._log_probability``); ``y``: ``(N,)`` one lightcurve shared by every ensemble, or ``(E, N)`` one
@@ -177,8 +180,11 @@ class DeviceEnsembleSampler(EnsembleSampler):
     ensemble axis.  ``block``: steps per kernel launch of ``sample`` (the generator yields once per block, with
     ``iteration`` advanced by the block; ``GPModelling.derive_posteriors`` sets it to its convergence interval)."""
 
-    def __init__(self, nwalkers, gp, y, yerr=None, ensembles=1, a=2.0, seed=None, block=100, frozen_mean=None):
+    def __init__(self, nwalkers, gp, y, yerr=None, ensembles=1, a=2.0, seed=None, block=100, frozen_mean=None, kernel="auto"):
         model = gp.device_model()
+        if kernel not in ("auto", "k8", "scan"):
+            raise ValueError("kernel must be 'auto', 'k8' or 'scan'")
+        self._kernel_flag = {"auto": 0, "k8": _native.FLAG_NO_SCAN, "scan": _native.FLAG_SCAN}[kernel]
         ndim = int(model.n_free)
         if nwalkers < 2 * ndim:
             raise ValueError("the number of walkers must be at least twice the dimension (got %d for ndim=%d)" % (nwalkers, ndim))
@@ -227,7 +233,7 @@ class DeviceEnsembleSampler(EnsembleSampler):
                                              _native.ptr(self._y), _native.ptr(self._diag), _native.ptr(self._means),
                                              _native.ptr(pos), _native.ptr(lp), int(init), int(nsteps), self.a, self._seed,
                                              int(self.iteration), _native.ptr(chain), _native.ptr(clp),
-                                             _native.ptr(self._accepted_i), self._flags)
+                                             _native.ptr(self._accepted_i), self._flags | self._kernel_flag)
         _native.check(rc)
         return chain, clp
 

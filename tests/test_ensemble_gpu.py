@@ -35,12 +35,12 @@ def _start(gp, W, rng, scale=0.05):
 def test_chain_log_prob_equals_k1_and_oracle():
     t, y, dy, ex, gp = _drw_problem()
     W = 16
-    s = DeviceEnsembleSampler(W, gp, y, seed=11, block=40)
+    s = DeviceEnsembleSampler(W, gp, y, seed=11, block=40, kernel="k8")
     s.run_mcmc(_start(gp, W, np.random.default_rng(0)), 80)
     chain = s.get_chain(); lp = s.get_log_prob()
     assert chain.shape == (80, W, 2) and lp.shape == (80, W)
     flat = chain.reshape(-1, 2)
-    k1 = gp.log_probability_batch(y, flat)
+    k1 = gp.log_probability_batch(y, flat, kernel="k1")
     np.testing.assert_allclose(lp.reshape(-1), k1, rtol=1e-13)
     ref = np.real(ogp.loglike_params([("drw",)], flat[::37], t, y, dy))
     np.testing.assert_allclose(lp.reshape(-1)[::37], ref, rtol=1e-10)
@@ -56,7 +56,7 @@ def test_reproducible_and_independent_of_block_size():
     chains = []
     for block in (7, 50, 200):
         np.random.seed(5)
-        s = DeviceEnsembleSampler(W, gp, y, seed=3, block=block)
+        s = DeviceEnsembleSampler(W, gp, y, seed=3, block=block, kernel="k8")
         s.run_mcmc(p0, 120)
         chains.append((s.get_chain().copy(), s.get_log_prob().copy()))
     for c, l in chains[1:]:

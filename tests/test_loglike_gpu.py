@@ -57,7 +57,7 @@ def test_loglike_matches_oracle(kind, N):
     p = p0[None, :] + np.random.default_rng(N).normal(0, 0.05, (70, len(p0)))
     if kind == "sho_overdamped+jitter":
         p[:, 1] = np.log(0.2) + np.random.default_rng(1).normal(0, 0.05, 70)     # stay below Q = 1/2
-    ll, status = gp.log_likelihood_batch(y, p, return_status=True)
+    ll, status = gp.log_likelihood_batch(y, p, return_status=True, kernel="k1")
     ref = ogp.loglike_params(spec, p, t, y, dy)
     assert np.all(status == 0)
     np.testing.assert_allclose(ll, ref, rtol=RTOL)
@@ -69,7 +69,7 @@ def test_sho_straddling_q_half_in_one_batch():
     gp.compute(t, dy + 1e-12)
     p = np.tile(gp.get_parameter_vector(), (64, 1))
     p[:, 1] = np.log(np.linspace(0.1, 3.0, 64))        # both regimes inside the same warps
-    ll = gp.log_likelihood_batch(y, p)
+    ll = gp.log_likelihood_batch(y, p, kernel="k1")
     spec = [("sho",), ("real",)]
     ref = np.concatenate([ogp.loglike_params(spec, p[i:i + 1], t, y, dy) for i in range(64)])
     np.testing.assert_allclose(ll, ref, rtol=RTOL)
@@ -83,17 +83,17 @@ def test_prior_and_not_positive_definite_status():
     p = np.tile(gp.get_parameter_vector(), (4, 1))
     p[1, 0] = 31.0        # above the upper bound of log_S0
     p[2, 3] = -6.0        # below the lower bound of log_Q
-    ll, status = gp.log_likelihood_batch(y, p, apply_prior=True, return_status=True)
+    ll, status = gp.log_likelihood_batch(y, p, apply_prior=True, return_status=True, kernel="k1")
     assert list(status) == [0, 3, 3, 0]
     assert np.isfinite(ll[0]) and ll[1] == -np.inf and ll[2] == -np.inf
     # without the prior the same points evaluate
-    ll2 = gp.log_likelihood_batch(y, p)
+    ll2 = gp.log_likelihood_batch(y, p, kernel="k1")
     np.testing.assert_allclose(ll2, ogp.loglike_params(spec, p, t, y, dy), rtol=RTOL)
     # a complex term violating a c >= b d is not positive definite -> -inf, status 1 (celerite LinAlgError)
     gp4 = GP(terms.ComplexTerm(-5.0, -8.0, -12.0, -12.5), mean=float(np.mean(y)))
     gp4.compute(t, dy + 1e-12)
     bad = np.array([[-5.0, 3.0, -12.0, -11.0]])
-    ll4, st4 = gp4.log_likelihood_batch(y, bad, return_status=True)
+    ll4, st4 = gp4.log_likelihood_batch(y, bad, return_status=True, kernel="k1")
     assert ll4[0] == -np.inf and st4[0] == 1
     gp4.set_parameter_vector(bad[0])
     with pytest.raises(np.linalg.LinAlgError):
@@ -121,7 +121,7 @@ def test_fitted_constant_mean():
     assert gp.vector_size == 3
     p = np.tile(gp.get_parameter_vector(), (33, 1))
     p[:, 2] += np.linspace(-0.1, 0.1, 33)
-    ll = gp.log_likelihood_batch(y, p)
+    ll = gp.log_likelihood_batch(y, p, kernel="k1")
     ref = ogp.loglike_params([("drw",)], p, t, y, dy, fit_mean=True)
     np.testing.assert_allclose(ll, ref, rtol=RTOL)
 
@@ -173,7 +173,7 @@ def test_large_batch_linearity_property():
     gp = GP(kernel, mean=mu)
     gp.compute(t, dy + 1e-12)
     p = c2_truth()[None, :] + np.random.default_rng(3).normal(0, 0.1, (B, 5))
-    ll = gp.log_likelihood_batch(y, p)
+    ll = gp.log_likelihood_batch(y, p, kernel="k1")
     k = 3.0
     gp2 = GP(build("drw+lor")[0], mean=k * mu)
     gp2.compute(t, k * (dy + 1e-12))
