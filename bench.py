@@ -371,30 +371,38 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
     ms = timed(k2, 3)
     out["loglike_grad"] = {"batch": Bg, "ms": ms, "evals_per_s": Bg / (ms * 1e-3),
                            "note": "forward + segment replay into shared memory + adjoint sweep; no O(N) tape in HBM"}
-    # the 32-parameter-set half-ensemble call of a 64-walker emcee step (latency bound by construction)
+    # the 32-parameter-set half-ensemble call of a 64-walker emcee step: K1 (one thread per series: the latency of the whole
+    # 1000-step chain) against K9 (parallel-in-time scan, one CTA per series: what the library picks for small batches)
     s_ll = torch.empty(32, dtype=torch.float64, device=dev); s_st = torch.empty(32, dtype=torch.int32, device=dev)
-    def k1_small():
-        _native.check(lib.mtg_loglike_dev(ctypes.byref(model), N_POINTS, 1, 32, 32, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
-                                          d_p.data_ptr(), s_ll.data_ptr(), s_st.data_ptr(), _native.FLAG_APPLY_PRIOR, stream.cuda_stream))
-    ms = timed(k1_small, 20)
-    out["half_ensemble_of_64_walkers"] = {"batch": 32, "ms": ms, "evals_per_s": 32 / (ms * 1e-3)}
-    # ---- the emcee loop of derive_posteriors on the device (kernel K8): one 64-walker ensemble as the reference runs it
-    #      (latency bound: steps/s), and 2368 ensembles in lock step (throughput: log-probability evaluations/s)
+    half = {"batch": 32}
+    for name, flag in (("k1_one_thread_per_series", _native.FLAG_NO_SCAN), ("k9_scan", _native.FLAG_SCAN), ("auto", 0)):
+        def k_small():
+            _native.check(lib.mtg_loglike_dev(ctypes.byref(model), N_POINTS, 1, 32, 32, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
+                                              d_p.data_ptr(), s_ll.data_ptr(), s_st.data_ptr(), _native.FLAG_APPLY_PRIOR | flag, stream.cuda_stream))
+        ms = timed(k_small, 20)
+        half[name] = {"ms": ms, "evals_per_s": 32 / (ms * 1e-3)}
+    out["half_ensemble_of_64_walkers"] = half
+    # ---- the emcee loop of derive_posteriors on the device: one 64-walker ensemble as the reference runs it (K10: one CTA
+    #      per proposal, scan likelihood, barrier per half step; K8 shown beside it), and 2368 ensembles in lock step (K8:
+    #      one thread per proposal, throughput regime: log-probability evaluations/s)
     try:
         W = WALKERS
         res = {}
-        for label, E, nsteps in (("one_ensemble_64_walkers", 1, 400), ("2368_ensembles_64_walkers", 2368, 20)):
-            pos = d_p[:E * W].clone().reshape(E, W, 5).contiguous()
-            lpw = torch.empty((E, W), dtype=torch.float64, device=dev)
-            acc = torch.zeros((E, W), dtype=torch.int32, device=dev)
+        for label, E, nsteps, flag in (("one_ensemble_64_walkers", 1, 2000, 0), ("one_ensemble_64_walkers_k8", 1, 400, _native.FLAG_NO_SCAN),
+                                       ("one_ensemble_12_walkers", 1, 2000, 0), ("2368_ensembles_64_walkers", 2368, 20, 0)):
+            Wl = 12 if "12_walkers" in label else W
+            pos = d_p[:E * Wl].clone().reshape(E, Wl, 5).contiguous()
+            lpw = torch.empty((E, Wl), dtype=torch.float64, device=dev)
+            acc = torch.zeros((E, Wl), dtype=torch.int32, device=dev)
             def k8():
-                _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N_POINTS, 1, E, W, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
+                _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N_POINTS, 1, E, Wl, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(), None,
                                                    pos.data_ptr(), lpw.data_ptr(), 1, nsteps, 2.0, 12345, 0, None, None, acc.data_ptr(), None, None,
-                                                   0, stream.cuda_stream))
+                                                   flag, stream.cuda_stream))
             ms = timed(k8, 2)
-            res[label] = {"ensembles": E, "walkers": W, "steps": nsteps, "ms": ms, "steps_per_s": nsteps / (ms * 1e-3),
-                          "logprob_evals_per_s": E * W * (nsteps + 1) / (ms * 1e-3),
+            res[label] = {"ensembles": E, "walkers": Wl, "steps": nsteps, "ms": ms, "steps_per_s": nsteps / (ms * 1e-3),
+                          "logprob_evals_per_s": E * Wl * (nsteps + 1) / (ms * 1e-3),
                           "acceptance": float(acc.double().mean().item()) / (3 * nsteps)}
+        res["reference_published"] = "163-221 emcee steps/s, 12 walkers, 15-process pool, N=1000 (BASELINE.md; unknown CPU)"
         out["ensemble_sampler"] = res
     except Exception as exc:
         out["ensemble_sampler"] = {"error": repr(exc)}

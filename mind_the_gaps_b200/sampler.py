@@ -225,10 +225,10 @@ class DeviceEnsembleSampler(EnsembleSampler):
         self._log_prob = np.empty(shape + (0, self.nwalkers))
         self._accepted_i = np.zeros((self.E, self.nwalkers), dtype=np.int32)
 
-    def _run(self, pos, lp, init, nsteps, store):
+    def _run(self, pos, lp, init, nsteps, store, chain=None, clp=None):
         E, W, nd = self.E, self.nwalkers, self.ndim
-        chain = np.empty((E, nsteps, W, nd)) if store else None
-        clp = np.empty((E, nsteps, W)) if store else None
+        if store and chain is None:
+            chain = np.empty((E, nsteps, W, nd)); clp = np.empty((E, nsteps, W))
         rc = _native.lib().mtg_ensemble_host(ctypes.byref(self._model), len(self._t), self._y.shape[0], E, W, _native.ptr(self._t),
                                              _native.ptr(self._y), _native.ptr(self._diag), _native.ptr(self._means),
                                              _native.ptr(pos), _native.ptr(lp), int(init), int(nsteps), self.a, self._seed,
@@ -255,14 +255,25 @@ class DeviceEnsembleSampler(EnsembleSampler):
         init = True
         done = 0
         iterations = int(iterations)
+        if store and E == 1:
+            # one ensemble: grow the emcee-shaped arrays once and let every launch write its block in place (K10 runs
+            # ~25 000 steps/s: re-concatenating the chain per block would cost more than the sampling)
+            have = self._chain.shape[0]
+            if have < self.iteration + iterations:
+                extra = self.iteration + iterations - have
+                self._chain = np.concatenate([self._chain, np.empty((extra, W, nd))], axis=0)
+                self._log_prob = np.concatenate([self._log_prob, np.empty((extra, W))], axis=0)
         while done < iterations:
             n = min(self.block, iterations - done)
-            chain, clp = self._run(p, lp, init, n, store)
+            if store and E == 1:
+                i0 = self.iteration
+                self._run(p, lp, init, n, True, self._chain[None, i0:i0 + n], self._log_prob[None, i0:i0 + n])
+            else:
+                chain, clp = self._run(p, lp, init, n, store)
+                if store:
+                    self._chain = np.concatenate([self._chain, chain], axis=1)
+                    self._log_prob = np.concatenate([self._log_prob, clp], axis=1)
             init = False
-            if store:
-                ax = 1 if E > 1 else 0
-                self._chain = np.concatenate([self._chain, chain if E > 1 else chain[0]], axis=ax)
-                self._log_prob = np.concatenate([self._log_prob, clp if E > 1 else clp[0]], axis=ax)
             self.iteration += n
             done += n
             yield (p if E > 1 else p[0]), (lp if E > 1 else lp[0])

@@ -34,4 +34,19 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k8_e
     python tools/k8_probe.py > gpurun_out/${TAG}_k8.log 2>&1
 export_rep ${TAG}_k8
 fi
+if [ "$WHAT" = all ] || [ "$WHAT" = ncu ] || [ "$WHAT" = ncu_scan ]; then
+export_rep() {   # name
+    ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1_ncu_full_raw.csv 2>/dev/null
+    ncu -i gpurun_out/$1.ncu-rep --page details > gpurun_out/$1_ncu_details.txt 2>/dev/null
+    ncu -i gpurun_out/$1.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/$1_ncu_source.csv.gz
+    rm -f gpurun_out/$1.ncu-rep
+}
+# K9 at B = 32 (the half ensemble of config C2): launches of the probe are 21 per batch size, B = 1, 6, 16, 32
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k9_loglike_scan -s 63 -c 1 -f -o gpurun_out/${TAG}_k9 \
+    python tools/k9_probe.py 1000 > gpurun_out/${TAG}_k9.log 2>&1
+export_rep ${TAG}_k9
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k10_ensemble_scan -s 1 -c 1 -f -o gpurun_out/${TAG}_k10 \
+    python tools/k10_probe.py > gpurun_out/${TAG}_k10.log 2>&1
+export_rep ${TAG}_k10
+fi
 du -sh gpurun_out; ls -la gpurun_out/
