@@ -425,11 +425,15 @@ struct Scratch {
 
 // log-likelihood of ONE series by the whole CTA (every thread calls it; every thread gets the result).
 // x: free parameter vector (any address space); ds: data-set column.  *st: 0 ok, 1 not positive definite, 2 non-finite.
-template <int JR, int JC, bool DUAL>
+// STAGED: t / yp / dp are shared-memory copies of the series (unit stride); otherwise global memory (yp, dp strided by S).
+template <int JR, int JC, bool DUAL, bool STAGED>
 __device__ __forceinline__ double series_loglike(const Plan &pl, const double *__restrict__ x, int N, const double *__restrict__ t,
                                                  const double *__restrict__ yp, const double *__restrict__ dp, size_t S,
                                                  bool ds_mean, double ds_mean_value, Scratch<JR + 2 * JC> &sc, int *st)
 {
+    auto T_ = [&](int n) { return STAGED ? t[n] : __ldg(t + n); };
+    auto Y_ = [&](int n) { return STAGED ? yp[n] : __ldg(yp + (size_t)n * S); };
+    auto D_ = [&](int n) { return STAGED ? dp[n] : __ldg(dp + (size_t)n * S); };
     constexpr int J = JR + 2 * JC;
     constexpr int NE = sizeof(Elem<J>) / sizeof(double);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -450,9 +454,9 @@ __device__ __forceinline__ double series_loglike(const Plan &pl, const double *_
         m.stationary(e.C);
     }
     for (int n = n0; n < n1; ++n) {
-        const double tn = __ldg(t + n);
-        const double dt = n > 0 ? tn - __ldg(t + n - 1) : 0.0;
-        append<JR, JC, DUAL>(m, e, dt, __ldg(yp + (size_t)n * S) - mean(tn), __ldg(dp + (size_t)n * S) + m.jit);
+        const double tn = T_(n);
+        const double dt = n > 0 ? tn - T_(n - 1) : 0.0;
+        append<JR, JC, DUAL>(m, e, dt, Y_(n) - mean(tn), D_(n) + m.jit);
     }
 
     // ---- phase 2: inclusive scan over the CTA ---------------------------------------------------------
@@ -518,16 +522,16 @@ __device__ __forceinline__ double series_loglike(const Plan &pl, const double *_
     }
     double chi2 = 0.0, prod = 1.0; int esum = 0; bool bad = false;
     for (int n = n0; n < n1; ++n) {
-        const double tn = __ldg(t + n);
-        const double dt = n > 0 ? tn - __ldg(t + n - 1) : 0.0;
+        const double tn = T_(n);
+        const double dt = n > 0 ? tn - T_(n - 1) : 0.0;
         typename Model<JR, JC, DUAL>::Trans F;
         m.transition(dt, F);
         m.template left<1>(F, mu);
         m.predict_cov(F, P);
         double Ph[J];
         m.Ph(P, Ph);
-        const double s = m.hdot(Ph) + __ldg(dp + (size_t)n * S) + m.jit;
-        const double v = __ldg(yp + (size_t)n * S) - mean(tn) - m.hdot(mu);
+        const double s = m.hdot(Ph) + D_(n) + m.jit;
+        const double v = Y_(n) - mean(tn) - m.hdot(mu);
         bad = bad || !(s > 0.0);
         const double rs = 1.0 / s;
         chi2 = fma(v * v, rs, chi2);
@@ -567,18 +571,37 @@ __device__ __forceinline__ double series_loglike(const Plan &pl, const double *_
     return sc.result;
 }
 
+// Series of up to K9_STAGE_MAX_N observations are copied to shared memory first (coalesced, one round of latency): every
+// thread then reads its observations twice (phases 1 and 3) -- and K10 once per proposal -- without touching L2 again.
+#define K9_STAGE_MAX_N 4096
+__device__ __forceinline__ void stage_series(double *sm, int N, const double *__restrict__ t, const double *__restrict__ yp,
+                                             const double *__restrict__ dp, size_t S)
+{
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        sm[n] = __ldg(t + n); sm[N + n] = __ldg(yp + (size_t)n * S); sm[2 * N + n] = __ldg(dp + (size_t)n * S);
+    }
+    __syncthreads();
+}
+
 template <int JR, int JC, bool DUAL>
 __global__ void __launch_bounds__(K9_THREADS, 1)
-k9_loglike_scan(const __grid_constant__ Plan pl, const BatchArgs a)
+k9_loglike_scan(const __grid_constant__ Plan pl, const BatchArgs a, int staged)
 {
     __shared__ Scratch<JR + 2 * JC> sc;
+    extern __shared__ double k9_series_sm[];          // [3][N] when staged
     const int b = blockIdx.x;
     const double *x = a.params + (size_t)b * pl.n_free;
     const bool inside = !(a.flags & MTG_FLAG_APPLY_PRIOR) || plan_in_prior(pl, x);
     const int ds = b / a.group;
     const bool dsm = (a.flags & MTG_FLAG_DS_MEAN) != 0;
     int st;
-    double ll = series_loglike<JR, JC, DUAL>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsm ? a.ds_mean[ds] : 0.0, sc, &st);
+    double ll;
+    if (staged) {
+        stage_series(k9_series_sm, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S);
+        ll = series_loglike<JR, JC, DUAL, true>(pl, x, a.N, k9_series_sm, k9_series_sm + a.N, k9_series_sm + 2 * a.N, 1, dsm,
+                                                dsm ? a.ds_mean[ds] : 0.0, sc, &st);
+    } else
+        ll = series_loglike<JR, JC, DUAL, false>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsm ? a.ds_mean[ds] : 0.0, sc, &st);
     if (threadIdx.x == 0) {
         if (!inside) { ll = -INFINITY; st = 3; }
         a.out_ll[b] = ll;
@@ -588,13 +611,28 @@ k9_loglike_scan(const __grid_constant__ Plan pl, const BatchArgs a)
 
 }  // namespace k9
 
+template <int JR, int JC, bool DUAL>
+static int launch_k9_one(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
+{
+    const int staged = a.N <= K9_STAGE_MAX_N;
+    const size_t dyn = staged ? sizeof(double) * 3 * (size_t)a.N : 0;
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !opted[dev]) {
+        MTG_CUDA(cudaFuncSetAttribute(k9::k9_loglike_scan<JR, JC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * 3 * K9_STAGE_MAX_N)));
+        opted[dev] = true;
+    }
+    k9::k9_loglike_scan<JR, JC, DUAL><<<a.B, K9_THREADS, dyn, stream>>>(pl, a, staged);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k9_loglike_scan launch");
+}
 template <int JR, int JC>
 static int launch_k9(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
 {
-    if (pl.has_sho) k9::k9_loglike_scan<JR, JC, true><<<a.B, K9_THREADS, 0, stream>>>(pl, a);
-    else            k9::k9_loglike_scan<JR, JC, false><<<a.B, K9_THREADS, 0, stream>>>(pl, a);
-    mtg_count_launch();
-    return mtg_cuda_check(cudaGetLastError(), "k9_loglike_scan launch");
+    if (pl.has_sho) return launch_k9_one<JR, JC, true>(pl, a, stream);
+    return launch_k9_one<JR, JC, false>(pl, a, stream);
 }
 
 // true when the scan kernel covers this model: <= 3 state dimensions and no Matern-3/2 slot
@@ -645,9 +683,10 @@ __device__ __forceinline__ void ens_barrier(unsigned *ctr, unsigned target)
 
 template <int JR, int JC, bool DUAL>
 __global__ void __launch_bounds__(K9_THREADS, 1)
-k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigned *barrier, double *cta_best)
+k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigned *barrier, double *cta_best, int staged)
 {
     __shared__ Scratch<JR + 2 * JC> sc;
+    extern __shared__ double k10_series_sm[];         // [3][N] when staged: the lightcurve is read from HBM / L2 once per CTA
     __shared__ uint32_t key[K10_MAX_W];
     __shared__ int32_t perm[K10_MAX_W];
     __shared__ double q[MTG_MAX_PARAMS], ps[MTG_MAX_PARAMS], bq[MTG_MAX_PARAMS];
@@ -665,10 +704,13 @@ k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigne
     const bool track_best = a.best_lp != nullptr;
     double my_best = -INFINITY;                        // thread 0: best log-probability this CTA has seen
 
+    if (staged) stage_series(k10_series_sm, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S);
     auto log_prob = [&](const double *x) -> double {   // CTA-collective; x in shared memory
         if (!plan_in_prior(pl, x)) return -INFINITY;   // uniform over the CTA
         int st;
-        return series_loglike<JR, JC, DUAL>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsv, sc, &st);
+        if (staged)
+            return series_loglike<JR, JC, DUAL, true>(pl, x, a.N, k10_series_sm, k10_series_sm + a.N, k10_series_sm + 2 * a.N, 1, dsm, dsv, sc, &st);
+        return series_loglike<JR, JC, DUAL, false>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsv, sc, &st);
     };
 
     // ---- initial log-probabilities: this CTA owns walkers slot and slot + H at the start ----------------
@@ -786,8 +828,12 @@ static int launch_k10_one(const Plan &pl, const EnsembleArgs &a, cudaStream_t st
     unsigned *barrier = reinterpret_cast<unsigned *>(scratch);
     double *cta_best = reinterpret_cast<double *>(scratch + off_best);
     Plan plc = pl; EnsembleArgs ac = a;
-    void *params[] = {&plc, &ac, &barrier, &cta_best};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k9::k10_ensemble_scan<JR, JC, DUAL>, dim3(a.E * H), dim3(K9_THREADS), params, 0, stream);
+    int staged = a.N <= K9_STAGE_MAX_N;
+    const size_t dyn = staged ? sizeof(double) * 3 * (size_t)a.N : 0;
+    MTG_CUDA(cudaFuncSetAttribute(k9::k10_ensemble_scan<JR, JC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * 3 * K9_STAGE_MAX_N)));
+    void *params[] = {&plc, &ac, &barrier, &cta_best, &staged};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k9::k10_ensemble_scan<JR, JC, DUAL>, dim3(a.E * H), dim3(K9_THREADS), params, dyn, stream);
     mtg_count_launch();
     cudaFreeAsync(scratch, stream);
     return mtg_cuda_check(e, "k10_ensemble_scan launch");
