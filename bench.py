@@ -121,7 +121,7 @@ def cpu_port_rate(n_sets_hint, seconds=10.0, nthreads=0):
     cref.loglike_params(spec, p[:256], t, y, dy, nthreads=nthreads)          # load + warm
     t0 = time.perf_counter(); cref.loglike_params(spec, p, t, y, dy, nthreads=nthreads); dt = time.perf_counter() - t0
     rate = len(p) / dt
-    n = int(min(max(rate * seconds, 4096), n_sets_hint))
+    n = int(max(rate * seconds, 4096))          # ~`seconds` of CPU work on all cores, whatever the GPU batch is
     t, y, dy, p, _ = workload(n, 98)
     t0 = time.perf_counter(); cref.loglike_params(spec, p, t, y, dy, nthreads=nthreads); dt = time.perf_counter() - t0
     return n / dt, n, dt, nthreads
@@ -406,6 +406,34 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
         out["ensemble_sampler"] = res
     except Exception as exc:
         out["ensemble_sampler"] = {"error": repr(exc)}
+    # ---- the calls a user of the reference makes on ONE lightcurve (configs[0]/[1] through the public API, host buffers):
+    #      GPModelling.fit (scipy L-BFGS-B, finite differences batched per request) and derive_posteriors (K10)
+    try:
+        import warnings
+        from mind_the_gaps_b200.gpmodelling import GPModelling
+        from mind_the_gaps_b200.lightcurves import GappyLightcurve
+        from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+        from helpers import C2_BOUNDS, c2_truth
+        tr = c2_truth()
+        lc1 = GappyLightcurve(t, y, dy)
+        api = {}
+        for label, mk in (("null_DRW", lambda: DampedRandomWalk(tr[0], tr[1], bounds=C2_BOUNDS[:2])),
+                          ("alt_DRW+Lorentzian", lambda: DampedRandomWalk(tr[0], tr[1], bounds=C2_BOUNDS[:2]) + Lorentzian(tr[2], tr[3], tr[4], bounds=C2_BOUNDS[2:]))):
+            g = GPModelling(lc1, mk())
+            g.fit()                                                   # warm-up
+            t0 = time.perf_counter(); sol = g.fit(g.initial_params); fit_s = time.perf_counter() - t0
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t0 = time.perf_counter()
+                g.derive_posteriors(fit=False, converge=False, max_steps=10000, convergence_steps=500, walkers=12, progress=False)
+                mc_s = time.perf_counter() - t0
+            api[label] = {"fit_ms": fit_s * 1e3, "fit_nfev": int(getattr(sol, "nfev", -1)), "fit_nit": int(sol.nit),
+                          "derive_posteriors_steps": int(g._sampler.iteration), "derive_posteriors_s": mc_s,
+                          "emcee_steps_per_s_incl_tau_checks": g._sampler.iteration / mc_s, "walkers": 12}
+        api["reference_published"] = "221 / 163 emcee it/s (null / alternative, 12 walkers, Pool(15)), tutorial_ppp.ipynb:132,210"
+        out["gpmodelling_public_api_one_lightcurve"] = api
+    except Exception as exc:
+        out["gpmodelling_public_api_one_lightcurve"] = {"error": repr(exc)}
     # ---- config C4: the full Protassov LRT, 10^4 simulations (DRW null vs Lorentzian + DRW alternative, N = 1000), sharded
     #      over the ranks (strong scaling: the total is fixed); simulate + fit null + fit alternative per simulation
     try:
@@ -563,8 +591,9 @@ def main():
             "gpu_launches": kernel_launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk.value, "unit": "TFLOP/s",
                          "frac": achieved_tf / pk.value if pk.value else None,
-                         "traffic": 15241728 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
-                         "traffic_source": "profiles/r01c_k1_loglike_ncu_full_raw.csv (ncu --set full, 378880 series), scaled to this batch",
+                         "traffic": 15289856 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
+                         "traffic_source": "profiles/r01g_k1_ncu_full_raw.csv (ncu --set full, 378880 series: dram__bytes_read 15.29 MB, "
+                                           "dram__bytes_write 0), scaled to this batch",
                          "kernel": "k1_loglike<1,1,false,true>",
                          "flops_per_eval": FLOPS_PER_EVAL, "flops_per_eval_computed_J3": FLOPS_PER_EVAL_COMPUTE,
                          "peak_source": "mtg_fp64_peak_probe: DFMA microbenchmark measured in this run "

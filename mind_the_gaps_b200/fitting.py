@@ -16,7 +16,7 @@ from scipy.optimize import OptimizeResult
 
 from . import _native
 
-__all__ = ["lbfgs_batch", "fit_lightcurves", "multistart_points", "s_statistic", "fit_psd_powerlaw"]
+__all__ = ["lbfgs_batch", "fit_lightcurves", "multistart_points", "scipy_lbfgsb", "s_statistic", "fit_psd_powerlaw"]
 
 _MESSAGES = {0: "CONVERGENCE: projected gradient / relative reduction below tolerance",
              1: "STOP: iteration limit reached",
@@ -70,6 +70,56 @@ def multistart_points(x_center, bounds, n_starts, rng, percent=0.1, spread=None)
     if n_starts > 1:
         out[:, 1:, :] += rng.normal(size=(P, n_starts - 1, nd)) * np.asarray(sig)[:, None, :]
     return np.clip(out, lo, hi).reshape(P * n_starts, nd)
+
+
+def _forward_steps(x, lo, hi, h0=1e-8):
+    """Absolute finite-difference steps as scipy's ``approx_derivative(method="2-point", abs_step=1e-8, bounds=...)``
+    takes them for L-BFGS-B without ``jac`` (``optimize._numdiff._adjust_scheme_to_bounds``): forward by ``h0``, backward
+    where the forward point leaves the box and the backward one fits, otherwise towards the farther bound."""
+    h = np.full(len(x), h0)
+    up, dn = hi - x, x - lo
+    fwd_ok, bwd_ok = up >= h0, dn >= h0
+    flip = ~fwd_ok & bwd_ok
+    h[flip] = -h0
+    neither = ~fwd_ok & ~bwd_ok
+    h[neither & (up >= dn)] = up[neither & (up >= dn)]
+    h[neither & (up < dn)] = -dn[neither & (up < dn)]
+    return h
+
+
+def scipy_lbfgsb(gp, y, x0, bounds=None, **options):
+    """``scipy.optimize.minimize(neg_log_like, x0, method="L-BFGS-B", bounds=...)`` exactly as ``GPModelling.fit`` calls
+    it in the reference (gpmodelling.py:192-193: no ``jac``, so scipy differentiates by 2-point finite differences with
+    an absolute step of 1e-8) -- with the ``ndim + 1`` likelihood evaluations of every function-and-gradient request
+    done in ONE batched device launch (the parallel-in-time kernel K9 for the narrow kernels: ~20 us) instead of
+    ``ndim + 1`` celerite calls.  Same optimiser, same finite-difference scheme, same ``OptimizeResult``.
+
+    ``gp``: a computed ``mind_the_gaps_b200.celerite.GP``; bounds default to ``gp.get_parameter_bounds()``."""
+    from scipy.optimize import minimize
+    if bounds is None:
+        bounds = gp.get_parameter_bounds()
+    lo = np.array([-np.inf if b[0] is None else b[0] for b in bounds], dtype=np.float64)
+    hi = np.array([np.inf if b[1] is None else b[1] for b in bounds], dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    nd = len(lo)
+
+    def fun_and_grad(x):
+        x = np.clip(np.asarray(x, dtype=np.float64), lo, hi)
+        h = _forward_steps(x, lo, hi)
+        X = np.repeat(x[None, :], nd + 1, axis=0)
+        X[1:][np.diag_indices(nd)] += h
+        hs = X[1:][np.diag_indices(nd)] - x                      # the step actually representable
+        ll = gp.log_likelihood_batch(y, X)
+        f = -ll[0]
+        if not np.isfinite(f):
+            return 1e25, np.zeros(nd)                            # celerite would raise LinAlgError here
+        with np.errstate(invalid="ignore", divide="ignore"):
+            g = -(ll[1:] - ll[0]) / hs
+        g[~np.isfinite(g)] = 0.0
+        return f, g
+
+    return minimize(fun_and_grad, np.asarray(x0, dtype=np.float64), jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),
+                    options=options or None)
 
 
 def fit_lightcurves(gp, t, Y, DY, x0=None, n_starts=1, rng=None, frozen_mean="lightcurve", spread=None, **opts):

@@ -5,11 +5,12 @@ Same constructor, methods, keyword arguments, properties and error behaviour as 
 class.  What changed underneath:
 
 * ``self.gp`` is ``mind_the_gaps_b200.celerite.GP`` (K1/K2 kernels) instead of ``celerite.GP``;
-* ``fit`` runs the batched device L-BFGS with analytic gradients (one problem here; the LRT driver
-  hands it thousands) and returns a ``scipy.optimize.OptimizeResult`` like ``scipy.optimize.minimize``;
+* ``fit`` is the reference's scipy L-BFGS-B call with every finite-difference gradient done as one batched launch
+  (``optimizer="device"``: the batched device L-BFGS with analytic gradients the LRT driver uses for thousands of fits);
 * ``derive_posteriors`` runs emcee's stretch-move loop inside ONE kernel launch per convergence interval
-  (``sampler.DeviceEnsembleSampler``, kernel K8; ``device_sampler=False`` keeps the host loop with one batched K1
-  launch per half step) -- ``cores`` is accepted and ignored, there is no process pool;
+  (``sampler.DeviceEnsembleSampler``: kernel K10 for the one-lightcurve case, K8 for thousands of ensembles;
+  ``device_sampler=False`` keeps the host loop with one batched launch per half step) -- ``cores`` is accepted and
+  ignored, there is no process pool;
 * ``generate_from_posteriors`` simulates all ``nsims`` lightcurves in one batched device call
   (``cpus`` accepted and ignored).
 """
@@ -85,17 +86,30 @@ class GPModelling(object):
         self.gp.set_parameter_vector(params)
         return -self.gp.log_likelihood(self._lightcurve.y)
 
-    def fit(self, initial_params=None, n_starts=1, **opts):
-        """Maximum-likelihood fit by (device) L-BFGS within ``gp.get_parameter_bounds()``; returns an
-        ``OptimizeResult`` (``x, fun, success, status, message, nit``) like ``scipy.optimize.minimize``."""
+    def fit(self, initial_params=None, n_starts=1, optimizer="auto", **opts):
+        """Maximum-likelihood fit within ``gp.get_parameter_bounds()``; returns an ``OptimizeResult`` like
+        ``scipy.optimize.minimize``.
+
+        ``optimizer="scipy"`` (the default for one start): the reference's own call -- scipy's L-BFGS-B with 2-point finite
+        differences (gpmodelling.py:192-193) -- every function-and-gradient request being one batched device launch
+        (``fitting.scipy_lbfgsb``).  ``optimizer="device"`` (the default for ``n_starts > 1``): the batched device L-BFGS
+        with analytic gradients that the LRT driver uses for thousands of lightcurves, best of the starts returned."""
         if initial_params is None:
             initial_params = self.initial_params
+        if optimizer == "auto":
+            optimizer = "scipy" if int(n_starts) <= 1 else "device"
+        if optimizer not in ("scipy", "device"):
+            raise ValueError("optimizer must be 'auto', 'scipy' or 'device'")
         lc = self._lightcurve
-        ds_mean = None
+        if optimizer == "scipy":
+            solution = fitting.scipy_lbfgsb(self.gp, lc.y, initial_params, **opts)
+            if np.all(np.isfinite(solution.x)):
+                self.gp.set_parameter_vector(solution.x)
+            return solution
         model = self.gp.device_model()
         starts = fitting.multistart_points(np.asarray(initial_params, dtype=np.float64), self.gp.get_parameter_bounds(),
                                            int(n_starts), np.random.default_rng(np.random.randint(0, 2 ** 31 - 1)))
-        res = fitting.lbfgs_batch(model, lc.times, lc.y, lc.dy, starts, int(n_starts), ds_mean=ds_mean, **opts)
+        res = fitting.lbfgs_batch(model, lc.times, lc.y, lc.dy, starts, int(n_starts), ds_mean=None, **opts)
         fun = np.where(np.isfinite(res["fun"]), res["fun"], np.inf)
         i = int(np.argmin(fun))
         st = int(res["status"][i])

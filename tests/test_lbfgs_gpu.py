@@ -87,3 +87,29 @@ def test_bounds_are_respected_when_optimum_is_outside():
         f = lambda p: -ogp.loglike_params([("drw",)], p[None, :], t, Y[s], DY[s])[0]
         ref = minimize(f, gp.get_parameter_vector(), method="L-BFGS-B", bounds=bounds)
         assert res[s].fun <= ref.fun + 1e-5 * abs(ref.fun) + 1e-6
+
+
+def test_scipy_driven_fit_follows_scipy_on_the_oracle():
+    """GPModelling.fit default path: scipy's L-BFGS-B with 2-point differences (the reference's own call), the ndim + 1
+    evaluations of each request batched in one launch -> the same iterates as scipy differentiating the oracle itself."""
+    from mind_the_gaps_b200.gpmodelling import GPModelling
+    from mind_the_gaps_b200.lightcurves import GappyLightcurve
+    S, N = 3, 300
+    t, Y, DY, truth = make_set(S, N, 43)
+    bounds = [(-15.0, 5.0), (-20.0, -5.0)]
+    for s in range(S):
+        lc = GappyLightcurve(t, Y[s], DY[s])
+        gpm = GPModelling(lc, DampedRandomWalk(truth[0] + 0.5, truth[1] - 0.5, bounds=bounds))
+        sol = gpm.fit()
+        f = lambda p: -ogp.loglike_params([("drw",)], p[None, :], t, Y[s], DY[s])[0]
+        ref = minimize(f, gpm.initial_params, method="L-BFGS-B", bounds=bounds)
+        assert sol.success == ref.success
+        assert abs(sol.fun - ref.fun) <= 1e-7 * abs(ref.fun)
+        np.testing.assert_allclose(sol.x, ref.x, atol=2e-4)
+        np.testing.assert_allclose(gpm.gp.get_parameter_vector(), sol.x)
+        dev = gpm.fit(gpm.initial_params, optimizer="device")
+        assert abs(dev.fun - sol.fun) <= 1e-5 * abs(sol.fun)
+    # a start on the upper bound differentiates backwards and stays inside the box
+    gpm = GPModelling(GappyLightcurve(t, Y[0], DY[0]), DampedRandomWalk(5.0, -5.0, bounds=bounds))
+    sol = gpm.fit()
+    assert np.all(sol.x >= [-15.0, -20.0]) and np.all(sol.x <= [5.0, -5.0]) and np.isfinite(sol.fun)
