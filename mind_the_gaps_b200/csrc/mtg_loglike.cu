@@ -22,8 +22,12 @@
 #ifndef K1_NARROW_J
 #define K1_NARROW_J 3
 #endif
-constexpr int k1_threads(int J) { return J <= K1_NARROW_J ? 256 : 128; }
-constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? 2 : 1; }
+#ifndef K1_NARROW_THREADS
+#define K1_NARROW_THREADS 256
+#define K1_NARROW_BLOCKS 2
+#endif
+constexpr int k1_threads(int J) { return J <= K1_NARROW_J ? K1_NARROW_THREADS : 128; }
+constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? K1_NARROW_BLOCKS : 1; }
 #ifndef K1_UNROLL
 #define K1_UNROLL 2
 #endif

@@ -55,6 +55,15 @@ def test_percent_zero_gives_exact_parameters():
         gpmodel.spread_walkers(5, parameters, bounds_drw + bounds_lor, percent=1.5)
 
 
+def test_max_attempts_with_impossibly_tight_bounds():          # gpmodelling_test.py:93-113
+    drw, lor = [5.0, 10.0], [10, 5, -5]
+    bounds_drw = [(v - 0.01, v + 0.01) for v in drw]; bounds_lor = [(v - 0.01, v + 0.01) for v in lor]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+    samples = gpmodel.spread_walkers(100, drw + lor, bounds_drw + bounds_lor, percent=0, max_attempts=50)
+    for i, sample in enumerate(samples.T):
+        assert np.all(sample == (drw + lor)[i])
+
+
 def test_gp_parameter_protocol():
     bounds_drw = [(4.0, 6.0), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
     gpmodel = _gpmodel(bounds_drw, bounds_lor)

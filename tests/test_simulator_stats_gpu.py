@@ -209,3 +209,26 @@ class TestFluxDistributions:                    # simulator_test.py:375-451 (+ K
         # the mean is exact on the full lightcurve; the 95 % segment may differ by the (red-noise) mean of the excluded 5 %
         assert abs(loc - self.inputmean) < 0.05
         assert abs(scale ** 2 - inputvar) < 0.01
+
+
+def test_segment_duration_and_sampling():        # simulator_test.py:255-304: cut_random_segment keeps duration and binning
+    np.random.seed(6)
+    for sim_dt in np.arange(0.01, 0.1, 1):       # (sic: the reference's range has the single value 0.01)
+        timestamps = np.arange(0, 10, sim_dt)
+        simu = Simulator(powerlaw(1.0), timestamps, sim_dt, 0.5, extension_factor=50)
+        lc = simu.simulate_regularly_sampled()
+        duration = timestamps[-1] - timestamps[0]
+        cut = cut_random_segment(lc, duration)
+        duration_cut = (cut.time[-1] - cut.dt / 2) - (cut.time[0] + cut.dt / 2)
+        assert abs(duration_cut - duration) < sim_dt
+    timestamps = np.arange(1, 3.1, 1)
+    simu = Simulator(powerlaw(1.0), timestamps, 0.1, 50, extension_factor=50)
+    lc = simu.simulate_regularly_sampled()
+    cut = cut_random_segment(lc, timestamps[-1] - timestamps[0])
+    duration_cut = (cut.time[-1] - cut.dt / 2) - (cut.time[0] + cut.dt / 2)
+    assert abs(cut.tseg - duration_cut) < np.median(np.diff(timestamps))
+    for dt in (0.01, 0.1, 1):
+        timestamps = np.arange(0, 10, dt)
+        simu = Simulator(powerlaw(1.0), timestamps, dt, 0.5, extension_factor=50, aliasing_factor=1)
+        lc = simu.simulate_regularly_sampled()
+        assert cut_random_segment(lc, timestamps[-1] - timestamps[0]).dt == dt
