@@ -4,10 +4,10 @@ optimiser)").
 In the reference, the GP optimiser is ``GPModelling.fit``: one
 ``scipy.optimize.minimize(self._neg_log_like, x0, method="L-BFGS-B", bounds=gp.get_parameter_bounds())``
 call per lightcurve with finite-difference gradients
-(``/root/reference/mind_the_gaps/gpmodelling.py:172-194``); the reference's own ``fitting.py`` holds
-periodogram power-law fits with lmfit and is not on the GP path.  This module
-fits MANY lightcurves x MANY starting points in lock step with the device L-BFGS of
-``csrc/mtg_lbfgs.cu`` driven by the analytic gradient kernel.
+(``/root/reference/mind_the_gaps/gpmodelling.py:172-194``).  This module fits MANY lightcurves x MANY starting
+points in lock step with the device L-BFGS of ``csrc/mtg_lbfgs.cu`` driven by the analytic gradient kernel.  The
+reference's own ``fitting.py`` (periodogram power-law fits, done there with lmfit) is restated at
+the end of the file with the same function names and returns.
 """
 import ctypes
 
@@ -16,7 +16,8 @@ from scipy.optimize import OptimizeResult
 
 from . import _native
 
-__all__ = ["lbfgs_batch", "fit_lightcurves", "multistart_points", "scipy_lbfgsb", "s_statistic", "fit_psd_powerlaw"]
+__all__ = ["lbfgs_batch", "fit_lightcurves", "multistart_points", "scipy_lbfgsb", "chose_ls_model", "chose_frequency_range", "brokenpl",
+           "linear_fit_break", "linear_fit", "s_statistic", "s_stat_powerlaw", "minimize_powerlaw", "fit_lomb_scargle", "fit_psd_powerlaw"]
 
 _MESSAGES = {0: "CONVERGENCE: projected gradient / relative reduction below tolerance",
              1: "STOP: iteration limit reached",
@@ -160,24 +161,154 @@ def fit_lightcurves(gp, t, Y, DY, x0=None, n_starts=1, rng=None, frozen_mean="li
     return out
 
 
-# ---- periodogram helpers the simulator's validation needs (reference fitting.py:92-95, 140-178) -----
+# ---- periodogram fitting (the reference's own ``mind_the_gaps/fitting.py``: same names, arguments and returns) --------
+# The reference does these small fits with lmfit (not a dependency here): ``linear_fit`` / ``linear_fit_break`` are
+# restated as bounded least squares with scipy, returning an object with the lmfit attributes the reference's callers
+# read (``params[name].value / .stderr``, ``best_fit``, ``bic``, ``nvarys``, ``errorbars``, ``chisqr``).
 
-def s_statistic(powers, model_powers):
-    """Whittle statistic ``S = 2 sum(P/M + ln M)`` (reference fitting.py:92-95; Vaughan 2005)."""
-    powers = np.asarray(powers, dtype=np.float64); model_powers = np.asarray(model_powers, dtype=np.float64)
-    return 2.0 * np.sum(powers / model_powers + np.log(model_powers))
+class _Value(float):
+    """A float that also answers ``.value`` (the reference hands lmfit ``Parameter`` objects to its callers)."""
+    stderr = None
+
+    @property
+    def value(self):
+        return float(self)
+
+
+class _Params(dict):
+    def get(self, key, default=None):
+        return dict.get(self, key, default)
+
+
+class PeriodogramFit(object):
+    def __init__(self, names, values, stderr, residual, best_fit):
+        self.params = _Params()
+        for n, v, e in zip(names, values, stderr):
+            val = _Value(v); val.stderr = None if e is None or not np.isfinite(e) else float(e)
+            self.params[n] = val
+        self.nvarys = len(names)
+        self.ndata = len(residual)
+        self.chisqr = float(np.sum(residual ** 2))
+        self.redchi = self.chisqr / max(self.ndata - self.nvarys, 1)
+        self.best_fit = best_fit
+        self.errorbars = all(e is not None and np.isfinite(e) for e in stderr)
+        _neg2ll = self.ndata * np.log(max(self.chisqr, 1e-250) / self.ndata)       # lmfit's definitions
+        self.aic = _neg2ll + 2 * self.nvarys
+        self.bic = _neg2ll + np.log(self.ndata) * self.nvarys
+
+
+def _plain(x):
+    return np.asarray(x.value if hasattr(x, "unit") else x, dtype=np.float64)
+
+
+def _bounded_least_squares(fun, x0, lo, hi, names, x, y):
+    from scipy.optimize import least_squares
+    res = least_squares(lambda p: fun(x, *p) - y, x0, bounds=(lo, hi))
+    r = res.fun
+    dof = max(len(y) - len(x0), 1)
+    try:
+        cov = np.linalg.inv(res.jac.T @ res.jac) * (np.sum(r ** 2) / dof)
+        err = np.sqrt(np.diag(cov))
+    except np.linalg.LinAlgError:
+        err = [None] * len(x0)
+    return PeriodogramFit(names, res.x, err, r, fun(x, *res.x))
+
+
+def brokenpl(x, intercept, slope, x_break):
+    """Broken power law (in log-log) that flattens above the break (fitting.py:39-47)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x < x_break, intercept + slope * (x - x_break), intercept)
+
+
+def linear_fit_break(frequencies, powers):
+    """Straight line with a break in ln-ln space (fitting.py:50-68): slope in [-4, 0], break inside the sampled range."""
+    log_f, log_p = np.log(_plain(frequencies)), np.log(_plain(powers))
+    return _bounded_least_squares(brokenpl, [1.0, -1.0, np.mean(log_f)], [-np.inf, -4.0, np.min(log_f)], [np.inf, 0.0, np.max(log_f)],
+                                  ["intercept", "slope", "x_break"], log_f, log_p)
+
+
+def linear_fit(frequencies, powers):
+    """Straight line in log10-log10 space (fitting.py:71-89): ``pow_slope`` in [-4, 0.5], ``pow_intercept`` free."""
+    log_f, log_p = np.log10(_plain(frequencies)), np.log10(_plain(powers))
+    slope0, icpt0 = np.polyfit(log_f, log_p, 1) if len(log_f) > 1 else (-1.0, np.mean(log_p))
+    return _bounded_least_squares(lambda x, m, c: m * x + c, [min(max(slope0, -4.0), 0.5), icpt0], [-4.0, -np.inf], [0.5, np.inf],
+                                  ["pow_slope", "pow_intercept"], log_f, log_p)
+
+
+def chose_ls_model(frequencies, powers):
+    """Line with or without a break, by BIC (fitting.py:12-20)."""
+    outfit_break = linear_fit_break(frequencies, powers)
+    outfit = linear_fit(frequencies, powers)
+    if outfit_break.bic < outfit.bic:
+        print("Best fit model: Linear Fit with Break")
+        return outfit_break
+    print("Best fit model: Linear Fit")
+    return outfit
+
+
+def chose_frequency_range(frequencies, power):
+    """High-frequency end of the usable range = the break of the broken power law, when one is preferred (fitting.py:23-36)."""
+    best_model = chose_ls_model(frequencies, power)
+    if best_model.nvarys == 3:
+        maximum_frequency = float(np.exp(best_model.params.get("x_break")))
+        print("Break found in the LS: restricting high frequency range to %.3g (frequency units)" % maximum_frequency)
+    else:
+        print("No break found in the LS: High frequency range won't be modified.")
+        maximum_frequency = float(np.max(_plain(frequencies)))
+    return best_model, maximum_frequency
+
+
+def s_statistic(observed_powers, model_powers):
+    """Whittle statistic ``S = sum(ln M + P / M)`` -- Vaughan+2003 eq. A.3 (fitting.py:92-95)."""
+    observed_powers = np.asarray(observed_powers, dtype=np.float64); model_powers = np.asarray(model_powers, dtype=np.float64)
+    return np.sum(np.log(model_powers) + observed_powers / model_powers)
+
+
+def s_stat_powerlaw(x, frequencies, observed_powers):
+    """``S`` of the power law ``x[0] f^x[1]`` (fitting.py:98-101)."""
+    return s_statistic(observed_powers, x[0] * np.asarray(frequencies, dtype=np.float64) ** x[1])
+
+
+def minimize_powerlaw(frequencies, observed_powers):
+    """Power-law fit by minimising ``S`` (fitting.py:104-108): norm >= 0, slope in [-4, 0]."""
+    from scipy.optimize import minimize
+    res = minimize(s_stat_powerlaw, [np.mean(observed_powers), -1], args=(frequencies, observed_powers), bounds=((0, np.inf), (-4, 0)),
+                   method="L-BFGS-B")
+    return res.x
+
+
+def fit_lomb_scargle(frequencies, powers, sigma=1):
+    """Power-law fit of a Lomb-Scargle periodogram = straight line in log-log (fitting.py:111-137).  The reference takes
+    the uncertainties from lmfit's profile-likelihood ``conf_interval``; here they are ``sigma`` standard errors of the
+    least-squares fit (the same for a linear model with Gaussian residuals)."""
+    out_fit = linear_fit(frequencies, powers)
+    psd_slope = out_fit.params.get("pow_slope")
+    icpt = out_fit.params.get("pow_intercept")
+    psd_norm = 10 ** icpt
+    if out_fit.errorbars and sigma > 0:
+        psd_slope_err = abs(2 * sigma * psd_slope.stderr)
+        psd_norm_err = abs(10 ** (icpt + sigma * icpt.stderr) - 10 ** (icpt - sigma * icpt.stderr))
+    else:
+        psd_slope_err = 0
+        psd_norm_err = 0
+    return psd_slope, psd_slope_err, psd_norm, psd_norm_err
 
 
 def fit_psd_powerlaw(frequencies, powers):
-    """Least-squares straight line in log-log space with the ``0.25068`` bias correction of
-    Vaughan (2005) (reference fitting.py:140-178, there done with lmfit).  Returns
-    ``(slope, slope_err, log10_norm, log10_norm_err)``."""
-    x = np.log10(np.asarray(frequencies, dtype=np.float64))
-    yv = np.log10(np.asarray(powers, dtype=np.float64))
-    A = np.vstack([x, np.ones_like(x)]).T
-    coef, res, _, _ = np.linalg.lstsq(A, yv, rcond=None)
-    n = len(x)
-    dof = max(n - 2, 1)
-    sigma2 = float(np.sum((yv - A @ coef) ** 2)) / dof
-    cov = sigma2 * np.linalg.inv(A.T @ A)
-    return float(coef[0]), float(np.sqrt(cov[0, 0])), float(coef[1] + 0.25068), float(np.sqrt(cov[1, 1]))
+    """Power-law fit of a periodogram after Vaughan (2005): least squares in log10-log10 space, the ``+0.25068`` bias
+    correction of the normalisation and the analytic uncertainties of that paper (fitting.py:140-178).  The zero
+    frequency (and the Nyquist frequency of even data sets) must have been removed.  Returns ``(psd_slope, psd_slope_err,
+    psd_norm, psd_norm_err)``; ``psd_slope`` answers ``.value`` like the lmfit parameter the reference returns."""
+    out_fit = linear_fit(frequencies, powers)
+    n_prime = len(powers)
+    sigma_2 = np.pi ** 2 / (6 * np.log(10) ** 2)
+    log_f = np.log10(_plain(frequencies))
+    log_f_2_sum = np.sum(np.power(log_f, 2))
+    delta = n_prime * log_f_2_sum - np.sum(log_f) ** 2
+    psd_slope_err = np.sqrt(n_prime * sigma_2 / delta)
+    psd_log10norm_err = np.sqrt(sigma_2 * log_f_2_sum / delta)
+    psd_slope = out_fit.params.get("pow_slope")
+    lognorm = out_fit.params.get("pow_intercept") + 0.25068
+    psd_norm = 10 ** lognorm
+    psd_norm_err = psd_norm - 10 ** (lognorm - psd_log10norm_err)
+    return psd_slope, psd_slope_err, psd_norm, psd_norm_err

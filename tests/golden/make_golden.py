@@ -371,8 +371,25 @@ def gen_io(out):
     os.remove(tmp)
 
 
+def gen_fitting(out):
+    """The lmfit-free functions of the reference's fitting.py (s_statistic, s_stat_powerlaw, minimize_powerlaw, brokenpl)
+    on a synthetic periodogram; the lmfit-based ones cannot run here (lmfit is a placeholder)."""
+    from mind_the_gaps import fitting as rfit
+    rng = np.random.default_rng(3)
+    f = np.fft.rfftfreq(2000, 0.5)[1:-1]
+    model = 3.0 * f ** -1.3
+    p = model * rng.exponential(1.0, len(f))                    # chi^2_2-distributed periodogram around a power law
+    out["f"] = f; out["p"] = p; out["model"] = model
+    out["s_statistic"] = np.float64(rfit.s_statistic(p, model))
+    out["s_stat_powerlaw"] = np.float64(rfit.s_stat_powerlaw([2.5, -1.1], f, p))
+    out["minimize_powerlaw"] = np.asarray(rfit.minimize_powerlaw(f, p))
+    x = np.linspace(-3.0, 2.0, 23)
+    out["brokenpl_x"] = x
+    out["brokenpl"] = rfit.brokenpl(x, 1.5, -2.0, 0.25)
+
+
 def main():
-    for name, fn in (("simulator", gen_simulator), ("noise", gen_noise), ("gp", gen_gp), ("io", gen_io)):
+    for name, fn in (("simulator", gen_simulator), ("noise", gen_noise), ("gp", gen_gp), ("io", gen_io), ("fitting", gen_fitting)):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         out = {}
