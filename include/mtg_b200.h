@@ -282,6 +282,22 @@ int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
                       double *pos, double *lp, int init_lp, int nsteps, double a, uint64_t seed, uint64_t step0,
                       double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags);
 
+/* ---- batched periodograms of an ensemble ---------------------------------
+ * mtg_power_spectrum_host: |rfft(rate)|^2 of L regularly sampled lightcurves rates[L][n] -> out_power[L][n/2+1]
+ *   (replaces the per-lightcurve numpy.fft.rfft loops of tests/simulator_test.py:24-35 and
+ *   docs/notebooks/lomb_scargle_biases.ipynb).
+ * mtg_lombscargle_host: generalised Lomb-Scargle periodogram of L lightcurves y[L][N] sharing the times t[N], at the M
+ *   frequencies freqs[M] (cycles per unit of t) -> out_power[L][M]; fit_mean / center_data / normalization as
+ *   astropy.timeseries.LombScargle(t, y, fit_mean=, center_data=, normalization=).power(freqs) with unit errors, the call
+ *   the reference's notebook makes once per lightcurve. */
+#define MTG_LS_STANDARD 0
+#define MTG_LS_MODEL    1
+#define MTG_LS_LOG      2
+#define MTG_LS_PSD      3
+int mtg_power_spectrum_host(int L, int n, const double *rates, double *out_power);
+int mtg_lombscargle_host(int N, int L, int M, const double *t, const double *y, const double *freqs,
+                         int fit_mean, int center_data, int normalization, double *out_power);
+
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers for the *_host entry points (cudaMallocHost / cudaFreeHost). */
 int mtg_host_alloc(void **ptr, uint64_t bytes);

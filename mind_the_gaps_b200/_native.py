@@ -97,6 +97,9 @@ SIGNATURES = {
     "mtg_sim_create": (ctypes.c_int, [ctypes.POINTER(MtgSimConfig), ctypes.POINTER(ctypes.c_void_p)]),
     "mtg_sim_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mtg_sim_trim": (ctypes.c_int, []),
+    "mtg_power_spectrum_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "mtg_lombscargle_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "mtg_sim_generate_host": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mtg_sim_generate_dev": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "mtg_sim_add_noise_host": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),

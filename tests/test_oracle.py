@@ -89,3 +89,23 @@ def test_psd_lorentzian(Q, S0):
     w = np.arange(1, 1000)
     np.testing.assert_array_almost_equal(terms.psd_lorentzian(w, S0=S0, Q=Q, omega0=5),
                                          terms.psd([("lorentzian",)], [np.log(S0), np.log(Q), np.log(5)], w))
+
+
+@pytest.mark.parametrize("floating_mean", [False, True])
+def test_lombscargle_restatement_matches_scipy(floating_mean):
+    """oracle.periodogram (astropy's algorithm restated) against scipy.signal.lombscargle, an independent implementation:
+    'psd' normalisation with unit errors = scipy's unnormalised power; 'standard' = scipy's normalize=True."""
+    from scipy.signal import lombscargle as sp_ls
+    from oracle import periodogram as op
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 300.0, 180))
+    y = 3.0 + np.sin(2 * np.pi * 0.07 * t) + 0.5 * rng.normal(size=len(t))
+    f = np.linspace(0.005, 0.5, 97)
+    mine = op.lombscargle(t, y, f, fit_mean=floating_mean, center_data=True, normalization="psd")
+    ref = sp_ls(t, y, 2 * np.pi * f, normalize=False, floating_mean=floating_mean) if floating_mean else \
+        sp_ls(t, y - y.mean(), 2 * np.pi * f, normalize=False)
+    np.testing.assert_allclose(mine, ref, rtol=1e-9)
+    mine_n = op.lombscargle(t, y, f, fit_mean=floating_mean, center_data=True, normalization="standard")
+    ref_n = sp_ls(t, y, 2 * np.pi * f, normalize=True, floating_mean=floating_mean) if floating_mean else \
+        sp_ls(t, y - y.mean(), 2 * np.pi * f, normalize=True)
+    np.testing.assert_allclose(mine_n, ref_n, rtol=1e-9)
