@@ -13,6 +13,7 @@
 // time-major [N][S] arrays: a warp touches <= 32 consecutive doubles per step (coalesced) and the
 // next step's values are prefetched one step ahead.
 #include "mtg_recursion.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 // CTA shape per recursion width J = JR + 2 JC.  Every CTA carries 48 KB of lookup tables + <= 12 KB of tiles, so at
@@ -187,7 +188,7 @@ int mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
 static long long mtg_scan_max_batch()
 {
     static long long v = -1;
-    if (v < 0) { const char *e = getenv("MTG_SCAN_MAX_B"); v = e ? atoll(e) : 1024; }
+    if (v < 0) { const char *e = getenv("MTG_SCAN_MAX_B"); v = e ? atoll(e) : 4096; }
     return v;
 }
 
@@ -211,7 +212,10 @@ extern "C" int mtg_loglike_dev(const mtg_model_t *model, int N, int S, int group
     // the batch, K9's cost is ~12x the work spread over 256 threads.  Crossover measured at ~2000 series (N = 1000).
     const bool can_scan = mtg_k9_supports(pl);
     if ((flags & MTG_FLAG_SCAN) && !can_scan) { mtg_set_error("MTG_FLAG_SCAN: model not covered by the scan kernel"); return MTG_EUNSUP; }
-    const bool scan = (flags & MTG_FLAG_SCAN) || (can_scan && !(flags & MTG_FLAG_NO_SCAN) && N >= 64 && (long long)B * 64 <= mtg_scan_max_batch() * 64LL);
+    // measured crossover (profiles/README.md, tools/k9_probe.py): K9 wins up to ~2.9 N series (N = 1000) / ~3.7 N (N = 200);
+    // one wave of CTAs (148) is always a win for N >= 64
+    const long long scan_b = std::max(148LL, std::min(2LL * N, mtg_scan_max_batch()));
+    const bool scan = (flags & MTG_FLAG_SCAN) || (can_scan && !(flags & MTG_FLAG_NO_SCAN) && N >= 64 && (long long)B <= scan_b);
     if (scan) return mtg_k9_dispatch(pl, a, (cudaStream_t)stream);
     return mtg_k1_dispatch(pl, a, (cudaStream_t)stream);
 }

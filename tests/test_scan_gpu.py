@@ -76,7 +76,7 @@ def test_scan_is_the_automatic_choice_for_small_batches_and_k1_for_large():
     auto = gp.log_likelihood_batch(y, p)
     np.testing.assert_array_equal(auto, gp.log_likelihood_batch(y, p, kernel="scan"))
     np.testing.assert_allclose(auto, ogp.loglike_params(spec, p, t, y, dy), rtol=RTOL)
-    big = np.tile(p, (64, 1))                                  # 2048 series: above the scan threshold
+    big = np.tile(p, (128, 1))                                 # 4096 series: above the scan threshold (2 N)
     np.testing.assert_array_equal(gp.log_likelihood_batch(y, big), gp.log_likelihood_batch(y, big, kernel="k1"))
     # a model the scan kernel does not cover falls back silently in auto mode and refuses when forced
     gp7 = GP(build("3sho+real")[0], mean=float(np.mean(y)))
