@@ -17,7 +17,7 @@ from test_loglike_gpu import build
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
-# kernel structures with <= 3 state dimensions and no Matern-3/2 slot: what K9 covers
+# kernel structures with <= 3 state dimensions: what K9 covers
 SCAN_KINDS = ["drw", "drw+lor", "complex+real", "sho_overdamped+jitter", "complex4"]
 
 
@@ -38,7 +38,7 @@ def extra(kind):
     return build(kind)
 
 
-ALL_KINDS = SCAN_KINDS + ["sho_under", "sho+real", "3real", "bpl", "cos+real"]
+ALL_KINDS = SCAN_KINDS + ["sho_under", "sho+real", "3real", "bpl", "cos+real", "matern+real"]
 
 
 @pytest.mark.parametrize("kind", ALL_KINDS)
@@ -148,3 +148,21 @@ def test_scan_long_series_property():
     a = gp.log_likelihood_batch(y, p, kernel="scan"); b = gp.log_likelihood_batch(y, p, kernel="k1")
     assert np.all(np.isfinite(a))
     np.testing.assert_allclose(a, b, rtol=RTOL)
+
+
+@pytest.mark.parametrize("x", [0.1, 30.0, 1000.0])
+def test_scan_matern32_conditioning(x):
+    """celerite's Matern-3/2 term = complex term with d = eps, b / a = w0 / eps = x: the stationary covariance of the slot
+    in the scan kernel has condition number ~4 x^2.  Densely sampled series (lags ~ 1 / w0) so that it matters."""
+    rng = np.random.default_rng(int(x))
+    w0 = 0.01 * x                                     # eps = 0.01
+    N = 600
+    t = np.cumsum(rng.uniform(0.2, 3.0, N)) / w0
+    y = rng.normal(0.0, 1.0, N).cumsum() * 0.1 + rng.normal(0, 0.05, N)
+    dy = np.full(N, 0.05)
+    gp = GP(terms.Matern32Term(0.0, np.log(np.sqrt(3.0) / w0)), mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    p = gp.get_parameter_vector()[None, :] + rng.normal(0, 0.1, (16, 2))
+    ll = gp.log_likelihood_batch(y, p, kernel="scan")
+    ref = ogp.loglike_params([("matern32", 0.01)], p, t, y, dy)
+    np.testing.assert_allclose(ll, ref, rtol=1e-9)
