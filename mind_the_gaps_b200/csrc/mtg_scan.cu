@@ -70,7 +70,7 @@ __device__ __forceinline__ Elem<J> shfl_up(const Elem<J> &e, int delta, int widt
     return r;
 }
 
-// inverse of a J x J matrix with det >= 1 (I + C J with C, J positive semi-definite): closed forms, J <= 3
+// inverse of a J x J matrix with det >= 1 (I + C J with C, J positive semi-definite): closed forms, J <= 4
 template <int J> __device__ __forceinline__ void inverse(const double *T, double *M);
 template <> __device__ __forceinline__ void inverse<1>(const double *T, double *M) { M[0] = 1.0 / T[0]; }
 template <> __device__ __forceinline__ void inverse<2>(const double *T, double *M)
@@ -85,6 +85,23 @@ template <> __device__ __forceinline__ void inverse<3>(const double *T, double *
     M[0] = c00 * r; M[3] = c01 * r; M[6] = c02 * r;
     M[1] = (T[2] * T[7] - T[1] * T[8]) * r; M[4] = (T[0] * T[8] - T[2] * T[6]) * r; M[7] = (T[1] * T[6] - T[0] * T[7]) * r;
     M[2] = (T[1] * T[5] - T[2] * T[4]) * r; M[5] = (T[2] * T[3] - T[0] * T[5]) * r; M[8] = (T[0] * T[4] - T[1] * T[3]) * r;
+}
+
+template <> __device__ __forceinline__ void inverse<4>(const double *a, double *b)      // Laplace expansion by 2 x 2 minors
+{
+    const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+    const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+    const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+    const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+    const double r = 1.0 / (s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0);
+    b[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * r;    b[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * r;
+    b[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * r; b[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * r;
+    b[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * r;   b[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * r;
+    b[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * r; b[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * r;
+    b[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * r;    b[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * r;
+    b[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * r; b[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * r;
+    b[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * r;  b[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * r;
+    b[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * r; b[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * r;
 }
 
 // e_i (earlier) then e_j (later).  FULL = false: only b and C of the result are formed (exclusive prefix for phase 3).
@@ -635,12 +652,12 @@ static int launch_k9(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
     return launch_k9_one<JR, JC, false>(pl, a, stream);
 }
 
-// true when the scan kernel covers this model: <= 3 state dimensions.  (celerite's Matern-3/2 term is a complex term with
+// true when the scan kernel covers this model: <= 4 state dimensions.  (celerite's Matern-3/2 term is a complex term with
 // d = eps and b / a = w0 / eps: its stationary covariance a [[1, x], [x, 1 + 2 x^2]], x = w0 / eps, has condition number
 // ~4 x^2, harmless for any correlation length longer than a few hundred time units -- tests/test_scan_gpu.py.)
 bool mtg_k9_supports(const Plan &pl)
 {
-    return pl.jr + 2 * pl.jc <= 3 && pl.jr + 2 * pl.jc >= 1;
+    return pl.jr + 2 * pl.jc <= 4 && pl.jr + 2 * pl.jc >= 1 && pl.jr <= 3;       // same structures as K1's dispatch
 }
 
 #define K9_CASE(R, C) if (pl.jr == R && pl.jc == C) return launch_k9<R, C>(pl, a, stream);
@@ -648,6 +665,7 @@ bool mtg_k9_supports(const Plan &pl)
 int mtg_k9_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
 {
     K9_CASE(1, 0) K9_CASE(2, 0) K9_CASE(3, 0) K9_CASE(0, 1) K9_CASE(1, 1)
+    K9_CASE(2, 1) K9_CASE(0, 2)
     mtg_set_error("scan kernel: unsupported kernel structure: %d real + %d complex slots", pl.jr, pl.jc);
     return MTG_EUNSUP;
 }
@@ -849,6 +867,7 @@ static int launch_k10(const Plan &pl, const EnsembleArgs &a, cudaStream_t stream
 int mtg_k10_dispatch(const Plan &pl, const EnsembleArgs &a, cudaStream_t stream)
 {
     K10_CASE(1, 0) K10_CASE(2, 0) K10_CASE(3, 0) K10_CASE(0, 1) K10_CASE(1, 1)
+    K10_CASE(2, 1) K10_CASE(0, 2)
     mtg_set_error("scan sampler: unsupported kernel structure: %d real + %d complex slots", pl.jr, pl.jc);
     return MTG_EUNSUP;
 }

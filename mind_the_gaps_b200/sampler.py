@@ -171,7 +171,7 @@ class DeviceEnsembleSampler(EnsembleSampler):
     share the algorithm and the random streams: K8 (``csrc/mtg_ensemble.cu``, one thread per proposal: thousands of
     ensembles) and K10 (``csrc/mtg_scan.cu``, one CTA per proposal with the parallel-in-time likelihood and a barrier
     across CTAs per half step: the one-lightcurve case of ``derive_posteriors``); ``kernel="auto"`` lets the library
-    choose (K10 when all ``E * ceil(W/2)`` CTAs fit the device and the model has <= 3 state dimensions).
+    choose (K10 when all ``E * ceil(W/2)`` CTAs fit the device and the model has <= 4 state dimensions).
 
     ``gp``: a computed ``mind_the_gaps_b200.celerite.GP`` (its kernel / mean / bounds define the log-probability,
     i.e. ``GPModelling._log_probability``); ``y``: ``(N,)`` one lightcurve shared by every ensemble, or ``(E, N)`` one

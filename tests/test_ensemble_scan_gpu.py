@@ -115,3 +115,24 @@ def test_several_ensembles_each_on_its_own_lightcurve_and_running_maximum():
         assert abs(ref - blp[e]) <= 1e-10 * abs(ref)
         refs = ogp.loglike_params([("drw",)], chain[e, ::9].reshape(-1, 2), t, Y[e], DY[e])
         np.testing.assert_allclose(clp[e, ::9].reshape(-1), refs, rtol=1e-10)
+
+
+def test_four_state_dimensions_two_sho_terms():
+    """J = 4 (two SHO terms, the second one crossing Q = 1/2 inside the ensemble): K10 == K8 chain, oracle log-probabilities."""
+    from mind_the_gaps_b200.celerite import terms
+    t, y, dy, _ = fake_lightcurve(400, 5)
+    b = dict(log_S0=(-15, 5), log_Q=(-3, 4), log_omega0=(-16, -8))
+    gp = GP(terms.SHOTerm(-6.0, np.log(3.0), -12.0, bounds=b) + terms.SHOTerm(-7.0, np.log(0.5), -11.0, bounds=b), mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    W = 14
+    p0 = gp.get_parameter_vector()[None, :] + np.random.default_rng(3).normal(0, 0.05, (W, 6))
+    res = {}
+    for kern in ("scan", "k8"):
+        np.random.seed(5)
+        s = DeviceEnsembleSampler(W, gp, y, seed=9, block=30, kernel=kern)
+        s.run_mcmc(p0, 60)
+        res[kern] = (s.get_chain().copy(), s.get_log_prob().copy())
+    np.testing.assert_allclose(res["scan"][0], res["k8"][0], rtol=1e-9)
+    flat = res["scan"][0].reshape(-1, 6)[::41]
+    ref = np.concatenate([ogp.loglike_params([("sho",), ("sho",)], flat[i:i + 1], t, y, dy) for i in range(len(flat))])
+    np.testing.assert_allclose(res["scan"][1].reshape(-1)[::41], ref, rtol=1e-10)

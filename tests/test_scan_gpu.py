@@ -17,7 +17,7 @@ from test_loglike_gpu import build
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
-# kernel structures with <= 3 state dimensions: what K9 covers
+# kernel structures with <= 4 state dimensions: what K9 covers
 SCAN_KINDS = ["drw", "drw+lor", "complex+real", "sho_overdamped+jitter", "complex4"]
 
 
@@ -29,6 +29,11 @@ def extra(kind):
     if kind == "3real":
         return (terms.RealTerm(-6.0, -13.0) + terms.RealTerm(-7.0, -11.0) + terms.RealTerm(-5.0, -15.0),
                 [("real",), ("real",), ("real",)])
+    if kind == "2sho":                   # J = 4, both Q regimes in the second term across the batch
+        return (terms.SHOTerm(-6.0, np.log(3.0), -12.0) + terms.SHOTerm(-7.0, 0.0, -11.0), [("sho",), ("sho",)])
+    if kind == "2real+complex4":        # J = 4
+        return (terms.RealTerm(-6.0, -13.0) + terms.RealTerm(-7.0, -11.0) + terms.ComplexTerm(-5.0, -8.0, -12.0, -12.5),
+                [("real",), ("real",), ("complex4",)])
     if kind == "bpl":
         from mind_the_gaps_b200.models import BendingPowerlaw
         return BendingPowerlaw(-5.0, -7.0, -12.0), [("bendingpl",)]
@@ -38,7 +43,7 @@ def extra(kind):
     return build(kind)
 
 
-ALL_KINDS = SCAN_KINDS + ["sho_under", "sho+real", "3real", "bpl", "cos+real", "matern+real"]
+ALL_KINDS = SCAN_KINDS + ["sho_under", "sho+real", "3real", "bpl", "cos+real", "matern+real", "2sho", "2real+complex4"]
 
 
 @pytest.mark.parametrize("kind", ALL_KINDS)
@@ -56,9 +61,11 @@ def test_scan_matches_oracle_and_k1(kind, N):
         p[:, 1] = np.log(0.2) + np.random.default_rng(1).normal(0, 0.05, B)
     if kind == "sho+real":
         p[:, 1] = np.log(np.linspace(0.1, 3.0, B))          # both SHO regimes in one launch
+    if kind == "2sho":
+        p[:, 4] = np.log(np.linspace(0.1, 3.0, B))
     ll, status = gp.log_likelihood_batch(y, p, return_status=True, kernel="scan")
     # the oracle refuses batches straddling Q = 1/2: row by row there
-    ref = (np.concatenate([ogp.loglike_params(spec, p[i:i + 1], t, y, dy) for i in range(B)]) if kind == "sho+real"
+    ref = (np.concatenate([ogp.loglike_params(spec, p[i:i + 1], t, y, dy) for i in range(B)]) if kind in ("sho+real", "2sho")
            else ogp.loglike_params(spec, p, t, y, dy))
     assert np.all(status == 0)
     np.testing.assert_allclose(ll, ref, rtol=RTOL)
