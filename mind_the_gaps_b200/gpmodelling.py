@@ -263,6 +263,25 @@ class GPModelling(object):
         self._need(self._mcmc_samples)
         return self._tau
 
+    def gather_posteriors(self, device=None):
+        """Pool the posterior draws of replica chains over the ranks of an initialised ``torch.distributed`` group.
+
+        The ensemble of ONE lightcurve does not shard (its half steps are sequential), so on several GPUs every rank
+        runs ``derive_posteriors`` on its own replica (give the ranks different ``np.random`` seeds) and this call
+        all-gathers ``mcmc_samples`` and ``loglikelihoods`` (NCCL when ``device`` is a CUDA device, gloo on CPU): the only
+        communication of the sampling path.  Afterwards the result properties describe the pooled sample on every rank.
+        Returns the number of draws contributed by each rank."""
+        import torch.distributed as dist
+        from .lrt import all_gather_varlen
+        self._need(self._mcmc_samples)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return [len(self._mcmc_samples)]
+        rows = np.concatenate([self._mcmc_samples, self._loglikelihoods[:, None]], axis=1)
+        pooled, counts = all_gather_varlen(dist, rows, device)
+        self._mcmc_samples = np.ascontiguousarray(pooled[:, :-1])
+        self._loglikelihoods = np.ascontiguousarray(pooled[:, -1])
+        return counts
+
     # -- simulation from the posteriors -------------------------------------------------------------------------
     def generate_from_posteriors(self, nsims=10, cpus=8, pdf="Gaussian", extension_factor=2, sigma_noise=None):
         """``nsims`` lightcurves, each simulated from one random posterior sample of the kernel parameters

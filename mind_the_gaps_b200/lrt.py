@@ -22,7 +22,7 @@ from . import _native
 from .celerite import GP
 from .stats import lrt_pvalue, lrt_statistic
 
-__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts", "all_gather_rows"]
+__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts", "all_gather_rows", "all_gather_varlen"]
 
 
 class LRTResult(object):
@@ -62,6 +62,31 @@ def all_gather_rows(dist, local_rows, n_total, device=None):
     recv = [torch.empty_like(send) for _ in range(world)]
     dist.all_gather(recv, send)
     return np.concatenate([recv[r].cpu().numpy()[: counts[r][1] - counts[r][0]] for r in range(world)], axis=0)
+
+
+def all_gather_varlen(dist, local_rows, device=None):
+    """Concatenate row blocks of DIFFERENT lengths over the ranks, in rank order, on every rank (two all-gathers: the
+    lengths, then NaN-padded blocks).  Used to pool the posterior draws of independent replica chains: the ensemble
+    of one lightcurve does not shard, so every GPU runs its own chain and only the draws travel."""
+    import torch
+    world = dist.get_world_size()
+    local_rows = np.ascontiguousarray(np.atleast_2d(np.asarray(local_rows, dtype=np.float64)))
+    width = local_rows.shape[1]
+    n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64)
+    if device is not None:
+        n_local = n_local.to(device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(max(counts), 1)
+    pad = np.full((nmax, width), np.nan)
+    pad[:local_rows.shape[0]] = local_rows
+    send = torch.from_numpy(pad)
+    if device is not None:
+        send = send.to(device)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send)
+    return np.concatenate([recv[r].cpu().numpy()[:counts[r]] for r in range(world)], axis=0), counts
 
 
 def _bounds_arrays(gp):

@@ -59,3 +59,39 @@ def test_all_gather_rows_world2_gloo(n_total):
         assert np.array_equal(full[:, 0], np.arange(n_total)) and np.array_equal(full[:, 1], 10.0 * np.arange(n_total))
         owner = np.concatenate([np.full(b - a, k) for k, (a, b) in enumerate(lrt.shard_range(n_total, k, world) for k in range(world))])
         assert np.array_equal(full[:, 2], owner)
+
+
+def _worker_varlen(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mind_the_gaps_b200.gpmodelling import GPModelling
+        n = 5 + 3 * rank                                         # replicas keep different numbers of draws
+        g = GPModelling.__new__(GPModelling)                     # result container only: no device needed
+        g._mcmc_samples = np.arange(n * 2, dtype=float).reshape(n, 2) + 100 * rank
+        g._loglikelihoods = -np.arange(n, dtype=float) - 1000 * rank
+        counts = g.gather_posteriors()
+        q.put((rank, counts, g.mcmc_samples, g.loglikelihoods, g.max_loglikelihood, g.max_parameters))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replica_posteriors_are_pooled_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_varlen, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {r[0]: r[1:] for r in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp_s = np.concatenate([np.arange(10, dtype=float).reshape(5, 2), np.arange(16, dtype=float).reshape(8, 2) + 100])
+    exp_l = np.concatenate([-np.arange(5, dtype=float), -np.arange(8, dtype=float) - 1000])
+    for r in range(world):
+        counts, samples, ll, best, best_p = got[r]
+        assert counts == [5, 8]
+        assert np.array_equal(samples, exp_s) and np.array_equal(ll, exp_l)
+        assert best == 0.0 and np.array_equal(best_p, [0.0, 1.0])
