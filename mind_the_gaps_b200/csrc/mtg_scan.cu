@@ -836,6 +836,11 @@ template <int JR, int JC, bool DUAL>
 static int launch_k10_one(const Plan &pl, const EnsembleArgs &a, cudaStream_t stream)
 {
     const int H = (a.W + 1) / 2, nd = pl.n_free;
+    if ((2.0 * a.nsteps + 4.0) * H >= 4.0e9) {       // the per-ensemble barrier counts arrivals in 32 bits
+        mtg_set_error("mtg_ensemble_dev: %d steps per launch overflow the barrier counter of the scan sampler; use blocks of <= %d steps",
+                      a.nsteps, (int)(1.9e9 / H));
+        return MTG_EINVAL;
+    }
     const size_t nb = sizeof(unsigned) * (size_t)a.E, nbest = sizeof(double) * (size_t)a.E * H * (nd + 1);
     int rc = mtg_pool_setup();
     if (rc) return rc;
