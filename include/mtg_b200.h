@@ -108,11 +108,14 @@ int         mtg_set_device(int device);
  * terms that cannot influence the result (j_compute). */
 int mtg_model_width(const mtg_model_t *model, int *j_celerite, int *j_compute);
 
-/* ---- K1: batched log-likelihood ---------------------------------------------------------
+/* ---- K1 / K9: batched log-likelihood ----------------------------------------------------
  * Replaces, for B parameter sets at once, celerite.GP.set_parameter_vector + log_prior +
  * log_likelihood as called from GPModelling._log_probability (gpmodelling.py:127-152) and
  * GPModelling._neg_log_like (:155-169); i.e. celerite CholeskySolver.compute + dot_solve +
- * log_determinant fused into one pass.
+ * log_determinant fused into one pass.  Two kernels compute the same number: K1 (one thread per
+ * series: large batches) and K9 (one CTA per series, the N-step chain parallelised by an associative
+ * scan: <= max(148, 2N) series of a model with <= 4 state dimensions); the library picks,
+ * MTG_FLAG_SCAN / MTG_FLAG_NO_SCAN force either.
  *   out_ll[B]   log-likelihood (+ log-prior with MTG_FLAG_APPLY_PRIOR); -inf when status != 0
  *   status[B]   may be NULL
  *   ds_mean[S]  only read with MTG_FLAG_DS_MEAN                                             */
@@ -261,7 +264,11 @@ int mtg_predict_host(const mtg_model_t *model, int N, const double *t, const dou
  * Replaces the emcee 3.1.4 loop GPModelling.derive_posteriors drives (gpmodelling.py:247-264):
  * EnsembleSampler.sample -> RedBlueMove (two random halves) -> StretchMove (scale a) -> log-probability of the
  * half ensemble = GPModelling._log_probability (:127-152) -> accept / reject, for `nsteps` steps and E independent
- * ensembles in ONE launch (one CTA per ensemble; positions in shared memory).
+ * ensembles in ONE launch.  Two kernels walk the same chain from the same Philox streams: K8 (one CTA per ensemble, one
+ * thread per proposal, positions in shared memory: thousands of ensembles) and K10 (one CTA per PROPOSAL with the
+ * parallel-in-time log-probability, a barrier across the CTAs of an ensemble per half step, cooperative launch: the
+ * one-lightcurve case, taken when all E * ceil(W/2) CTAs fit the device and the model has <= 4 state dimensions;
+ * MTG_FLAG_SCAN / MTG_FLAG_NO_SCAN force either).
  *   S        1: every ensemble samples the same lightcurve; E: ensemble e samples data set e (y, diag [N][S])
  *   pos      [E][W][ndim] walker positions, updated in place;  lp [E][W] their log-probabilities
  *   init_lp  non-zero: lp is computed from pos first (start of a run); zero: lp is read (continuation)
