@@ -109,3 +109,33 @@ def test_lombscargle_restatement_matches_scipy(floating_mean):
     ref_n = sp_ls(t, y, 2 * np.pi * f, normalize=True, floating_mean=floating_mean) if floating_mean else \
         sp_ls(t, y - y.mean(), 2 * np.pi * f, normalize=True)
     np.testing.assert_allclose(mine_n, ref_n, rtol=1e-9)
+
+
+@pytest.mark.parametrize("spec,p0", [
+    ([("drw",), ("lorentzian",)], None),
+    ([("sho",)], [-6.0, np.log(3.0), np.log(2 * np.pi / (30 * 86400))]),
+    ([("sho",)], [-6.0, np.log(0.3), np.log(2 * np.pi / (30 * 86400))]),
+    ([("complex4",), ("real",)], [-7.0, -8.5, -14.0, -12.5, -6.0, -15.0]),
+    ([("matern32", 0.01)], [-3.0, 14.0]),
+    ([("sho",), ("sho",)], [-6.0, np.log(3.0), -12.0, -7.0, np.log(2.0), -11.0]),
+])
+def test_kalman_and_scan_forms_equal_the_dense_likelihood(spec, p0):
+    """The formulation behind kernels K9 / K10: state-space model of a celerite kernel, sequential Kalman filter, and the
+    parallel-in-time scan, against the dense Cholesky oracle -- also with measurement errors of zero."""
+    from oracle import kalman, terms as ot
+    from helpers import c2_truth, fake_lightcurve
+    t, y, dy, _ = fake_lightcurve(300, 2)
+    p = np.asarray(c2_truth() if p0 is None else p0, dtype=float)
+    co = ot.coefficients(spec, p)
+    ar, cr, ac, bc, cc, dc = [np.atleast_1d(np.asarray(x, dtype=float)) for x in co[:6]]
+    jit = float(co[6]) if len(co) > 6 else 0.0
+    r = y - np.mean(y)
+    for scale in (1.0, 0.0):
+        diag = (dy * scale + 1e-12) ** 2
+        if scale:
+            ref = gp.loglike_dense(t, r, diag, ar, cr, ac, bc, cc, dc, jitter=jit)
+        else:
+            ref = float(np.ravel(np.real(gp.loglike_recursion(t, r, diag, ar, cr, ac, bc, cc, dc, jitter=jit)))[0])
+        model = kalman.statespace(ar, cr, ac, bc, cc, dc)
+        assert abs(kalman.loglike_sequential(t, r, diag + jit, model) - ref) <= 1e-11 * abs(ref)
+        assert abs(kalman.loglike_scan(t, r, diag + jit, model, threads=64) - ref) <= 1e-11 * abs(ref)
