@@ -591,8 +591,8 @@ def main():
             "gpu_launches": kernel_launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk.value, "unit": "TFLOP/s",
                          "frac": achieved_tf / pk.value if pk.value else None,
-                         "traffic": 15289856 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
-                         "traffic_source": "profiles/r01g_k1_ncu_full_raw.csv (ncu --set full, 378880 series: dram__bytes_read 15.29 MB, "
+                         "traffic": 15287808 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
+                         "traffic_source": "profiles/r01j_k1_ncu_full_raw.csv (ncu --set full, 378880 series: dram__bytes_read 15.29 MB, "
                                            "dram__bytes_write 0), scaled to this batch",
                          "kernel": "k1_loglike<1,1,false,true>",
                          "flops_per_eval": FLOPS_PER_EVAL, "flops_per_eval_computed_J3": FLOPS_PER_EVAL_COMPUTE,
