@@ -302,6 +302,10 @@ int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
 #define MTG_LS_LOG      2
 #define MTG_LS_PSD      3
 int mtg_power_spectrum_host(int L, int n, const double *rates, double *out_power);
+/* Normalised autocorrelation functions of L series x[L][n_t] -> out_acf[L][n_t] (emcee autocorr.function_1d: mean removed,
+ * zero padded to 2 * 2^k, FFT, |.|^2, inverse FFT, divided by lag 0): the convergence diagnostic of
+ * GPModelling.derive_posteriors (gpmodelling.py:251-263 -> emcee get_autocorr_time) for all walkers and dimensions at once. */
+int mtg_autocorr_host(int L, int n_t, const double *x, double *out_acf);
 int mtg_lombscargle_host(int N, int L, int M, const double *t, const double *y, const double *freqs,
                          int fit_mean, int center_data, int normalization, double *out_power);
 

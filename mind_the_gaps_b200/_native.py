@@ -98,6 +98,7 @@ SIGNATURES = {
     "mtg_sim_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mtg_sim_trim": (ctypes.c_int, []),
     "mtg_power_spectrum_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "mtg_autocorr_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "mtg_lombscargle_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "mtg_sim_generate_host": (ctypes.c_int, [_vp, ctypes.c_int, _mp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -227,3 +227,81 @@ extern "C" int mtg_power_spectrum_host(int L, int n, const double *rates_rows, d
     cudaStreamDestroy(st);
     return rc;
 }
+
+// ---- autocorrelation functions of chains (emcee autocorr.function_1d, batched) ------------------------
+// GPModelling.derive_posteriors checks convergence every `convergence_steps` steps on the integrated autocorrelation
+// time of the WHOLE chain so far (gpmodelling.py:251-263 -> emcee get_autocorr_time): walkers x ndim FFTs of the chain
+// length.  With the sampler itself at ~25 000 steps/s that host computation became the bottleneck of the call, so the
+// device sampler computes the normalised autocorrelation functions here: mean removal + zero padding to 2 * 2^k, D2Z,
+// |.|^2, Z2D, normalisation by lag 0 -- emcee's function_1d for all series at once.
+__global__ void k_acf_center_pad(int n_t, int nfft, const double *__restrict__ x /*[L][n_t]*/, double *__restrict__ out /*[L][nfft]*/)
+{
+    __shared__ double red[32];
+    const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const double *row = x + (size_t)l * n_t;
+    double s = 0.0;
+    for (int i = tid; i < n_t; i += blockDim.x) s += row[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < nw; ++w) tot += red[w];
+    const double m = tot / n_t;
+    double *o = out + (size_t)l * nfft;
+    for (int i = tid; i < nfft; i += blockDim.x) o[i] = i < n_t ? row[i] - m : 0.0;
+}
+__global__ void k_acf_power(size_t n, double2 *__restrict__ z)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 v = z[i]; z[i] = make_double2(v.x * v.x + v.y * v.y, 0.0); }
+}
+__global__ void k_acf_normalise(int n_t, int nfft, const double *__restrict__ r /*[L][nfft]*/, double *__restrict__ out /*[L][n_t]*/)
+{
+    const int l = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_t) out[(size_t)l * n_t + i] = r[(size_t)l * nfft + i] / r[(size_t)l * nfft];
+}
+
+extern "C" int mtg_autocorr_host(int L, int n_t, const double *x_rows, double *out_acf)
+{
+    if (L < 1 || n_t < 1 || !x_rows || !out_acf) { mtg_set_error("mtg_autocorr_host: bad argument"); return MTG_EINVAL; }
+    int nfft = 2;
+    while (nfft < 2 * n_t) nfft <<= 1;                     // 2 * next power of two >= n_t, as emcee pads
+    const int Mh = nfft / 2 + 1;
+    cudaStream_t st = nullptr;
+    MTG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    double *d_x = nullptr, *d_pad = nullptr, *d_out = nullptr; double2 *d_spec = nullptr;
+    cufftHandle fwd = 0, inv = 0;
+    int rc = 0;
+    if (cudaMalloc((void **)&d_x, sizeof(double) * (size_t)L * n_t) != cudaSuccess ||
+        cudaMalloc((void **)&d_pad, sizeof(double) * (size_t)L * nfft) != cudaSuccess ||
+        cudaMalloc((void **)&d_spec, sizeof(double2) * (size_t)L * Mh) != cudaSuccess ||
+        cudaMalloc((void **)&d_out, sizeof(double) * (size_t)L * n_t) != cudaSuccess) { mtg_set_error("mtg_autocorr_host: out of memory"); rc = MTG_ENOMEM; }
+    int nn[1] = {nfft};
+    if (!rc && (cufftPlanMany(&fwd, 1, nn, nullptr, 1, nfft, nullptr, 1, Mh, CUFFT_D2Z, L) != CUFFT_SUCCESS ||
+                cufftPlanMany(&inv, 1, nn, nullptr, 1, Mh, nullptr, 1, nfft, CUFFT_Z2D, L) != CUFFT_SUCCESS)) {
+        mtg_set_error("mtg_autocorr_host: cufftPlanMany(n=%d, batch=%d) failed", nfft, L); rc = MTG_ENOMEM;
+    }
+    if (!rc) {
+        cufftSetStream(fwd, st); cufftSetStream(inv, st);
+        cudaMemcpyAsync(d_x, x_rows, sizeof(double) * (size_t)L * n_t, cudaMemcpyHostToDevice, st);
+        k_acf_center_pad<<<L, 256, 0, st>>>(n_t, nfft, d_x, d_pad);
+        if (cufftExecD2Z(fwd, d_pad, (cufftDoubleComplex *)d_spec) != CUFFT_SUCCESS) { mtg_set_error("cufftExecD2Z failed"); rc = MTG_EINVAL; }
+    }
+    if (!rc) {
+        const size_t tot = (size_t)L * Mh;
+        k_acf_power<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, d_spec);
+        if (cufftExecZ2D(inv, (cufftDoubleComplex *)d_spec, d_pad) != CUFFT_SUCCESS) { mtg_set_error("cufftExecZ2D failed"); rc = MTG_EINVAL; }
+    }
+    if (!rc) {
+        k_acf_normalise<<<dim3((n_t + 255) / 256, L), 256, 0, st>>>(n_t, nfft, d_pad, d_out);
+        mtg_count_launch(3);
+        cudaMemcpyAsync(out_acf, d_out, sizeof(double) * (size_t)L * n_t, cudaMemcpyDeviceToHost, st);
+        rc = mtg_cuda_check(cudaStreamSynchronize(st), "mtg_autocorr_host sync");
+    }
+    if (fwd) cufftDestroy(fwd);
+    if (inv) cufftDestroy(inv);
+    cudaFree(d_x); cudaFree(d_pad); cudaFree(d_spec); cudaFree(d_out);
+    cudaStreamDestroy(st);
+    return rc;
+}

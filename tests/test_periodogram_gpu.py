@@ -59,3 +59,22 @@ def test_lomb_scargle_bias_study_shape():
     uneven = np.array([float(fit_lomb_scargle(f, pl, sigma=0)[0]) for pl in ls])
     assert abs(np.mean(even) + 1.0) < 0.1
     assert np.all(np.isfinite(uneven)) and -1.5 < np.mean(uneven) < -0.3        # flatter: power leaks to high frequencies
+
+
+@pytest.mark.parametrize("n_t", [1, 500, 4096, 20001])
+def test_device_autocorrelation_matches_emcee_function_1d(n_t):
+    """mtg_autocorr_host (the convergence diagnostic of the device sampler) against the host restatement of emcee's
+    function_1d, and the integrated autocorrelation times that follow from both."""
+    from mind_the_gaps_b200 import sampler
+    rng = np.random.default_rng(n_t)
+    x = np.empty((n_t, 6, 3))
+    x[0] = rng.normal(size=(6, 3))
+    rho = np.array([0.5, 0.9, 0.99])
+    for i in range(1, n_t):                                # AR(1) chains with different correlation lengths per dimension
+        x[i] = rho * x[i - 1] + np.sqrt(1 - rho ** 2) * rng.normal(size=(6, 3))
+    if n_t > 1:
+        dev = sampler._mean_acf_device(x); host = sampler._mean_acf(x)
+        np.testing.assert_allclose(dev, host, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(sampler.integrated_time(x, tol=0, acf=sampler._mean_acf_device), sampler.integrated_time(x, tol=0), rtol=1e-9)
+    else:
+        assert np.all(np.isnan(sampler._mean_acf_device(x)) | (sampler._mean_acf_device(x) == 1.0))
