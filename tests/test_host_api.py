@@ -182,3 +182,22 @@ def test_integrated_time_of_ar1():
         x[i] = rho * x[i - 1] + rng.normal(size=(4, 1))
     tau = integrated_time(x, tol=0)
     assert abs(tau[0] - (1 + rho) / (1 - rho)) < 3.0
+
+
+def test_finite_difference_steps_follow_scipy_at_the_bounds():
+    """fitting._forward_steps: the absolute 2-point steps scipy's L-BFGS-B takes without ``jac`` (1e-8 forward, backward
+    at an upper bound, towards the farther bound in a box narrower than the step) -- checked against
+    scipy.optimize._numdiff.approx_derivative on a function whose gradient is known."""
+    from scipy.optimize._numdiff import approx_derivative
+    from mind_the_gaps_b200.fitting import _forward_steps
+    lo = np.array([-1.0, 0.0, 2.0, -np.inf, 0.0]); hi = np.array([1.0, 5.0, 2.0 + 1.2e-8, np.inf, 5e-9])
+    x = np.array([0.3, 5.0, 2.0 + 1.0e-8, 7.0, 1e-9])
+    h = _forward_steps(x, lo, hi)
+    assert h[0] == 1e-8 and h[1] == -1e-8 and h[3] == 1e-8
+    assert h[2] < 0 and abs(h[2]) <= 1.0e-8 + 1e-20          # neither side fits: towards the farther (lower) bound
+    assert h[4] > 0 and h[4] <= 4e-9 + 1e-20
+    assert np.all(x + h >= lo) and np.all(x + h <= hi)
+    f = lambda z: np.sum(z ** 2) + z[0] * z[1]
+    mine = np.array([(f(x + np.eye(5)[k] * ((x + np.eye(5)[k] * h[k])[k] - x[k])) - f(x)) / ((x + np.eye(5)[k] * h[k])[k] - x[k]) for k in range(5)])
+    ref = approx_derivative(f, x, method="2-point", abs_step=1e-8, bounds=(lo, hi))
+    np.testing.assert_allclose(mine[[0, 1, 3]], ref[[0, 1, 3]], rtol=1e-12)      # where the plain step fits, identical to scipy
