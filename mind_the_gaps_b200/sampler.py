@@ -308,8 +308,10 @@ class DeviceEnsembleSampler(EnsembleSampler):
         return v
 
     def get_autocorr_time(self, discard=0, thin=1, **kwargs):
-        kwargs.setdefault("acf", _mean_acf_device)
         ch = self.get_chain(discard=discard, thin=thin)
+        # short chains: the host FFTs cost less than the trip to the device
+        if ch.shape[-3] * ch.shape[-2] * ch.shape[-1] >= 60000:
+            kwargs.setdefault("acf", _mean_acf_device)
         if self.E == 1:
             return thin * integrated_time(ch, **kwargs)
         return np.array([thin * integrated_time(ch[e], **kwargs) for e in range(self.E)])
