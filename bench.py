@@ -421,6 +421,9 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
                           ("alt_DRW+Lorentzian", lambda: DampedRandomWalk(tr[0], tr[1], bounds=C2_BOUNDS[:2]) + Lorentzian(tr[2], tr[3], tr[4], bounds=C2_BOUNDS[2:]))):
             g = GPModelling(lc1, mk())
             g.fit()                                                   # warm-up
+            with warnings.catch_warnings():                           # warm-up of the sampler / cuFFT (first use loads the library)
+                warnings.simplefilter("ignore")
+                g.derive_posteriors(fit=False, converge=False, max_steps=6000, convergence_steps=2000, walkers=12, progress=False)
             t0 = time.perf_counter(); sol = g.fit(g.initial_params); fit_s = time.perf_counter() - t0
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")

@@ -16,6 +16,7 @@
 //     unit weights -- restated in oracle/periodogram.py and pinned there on scipy.signal.lombscargle(floating_mean=...).
 #include "mtg_common.cuh"
 #include <cufft.h>
+#include <mutex>
 
 #define LS_TILE 64
 #define LS_KT 16
@@ -262,46 +263,76 @@ __global__ void k_acf_normalise(int n_t, int nfft, const double *__restrict__ r 
     if (i < n_t) out[(size_t)l * n_t + i] = r[(size_t)l * nfft + i] / r[(size_t)l * nfft];
 }
 
+// Plans and buffers of the autocorrelation entry are kept between calls (derive_posteriors calls it every few hundred
+// steps with a slowly growing chain: the padded length changes only at powers of two): plan creation and cudaMalloc cost
+// more than the transforms themselves.
+struct AcfCtx {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t st = nullptr;
+    int nfft = 0, L = 0;
+    cufftHandle fwd = 0, inv = 0;
+    double *d_x = nullptr, *d_pad = nullptr, *d_out = nullptr; double2 *d_spec = nullptr;
+    size_t cap_x = 0, cap_out = 0, cap_pad = 0, cap_spec = 0;
+    void drop_plans() { if (fwd) cufftDestroy(fwd); if (inv) cufftDestroy(inv); fwd = inv = 0; nfft = L = 0; }
+    void drop_all()
+    {
+        drop_plans();
+        cudaFree(d_x); cudaFree(d_pad); cudaFree(d_out); cudaFree(d_spec);
+        d_x = d_pad = d_out = nullptr; d_spec = nullptr; cap_x = cap_out = cap_pad = cap_spec = 0;
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
+};
+static AcfCtx g_acf;
+
+static int acf_grow(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return 0;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    const size_t want = bytes + bytes / 2;
+    if (cudaMalloc(p, want) != cudaSuccess) { mtg_set_error("mtg_autocorr_host: out of memory (%zu bytes)", want); return MTG_ENOMEM; }
+    *cap = want;
+    return 0;
+}
+
 extern "C" int mtg_autocorr_host(int L, int n_t, const double *x_rows, double *out_acf)
 {
     if (L < 1 || n_t < 1 || !x_rows || !out_acf) { mtg_set_error("mtg_autocorr_host: bad argument"); return MTG_EINVAL; }
     int nfft = 2;
     while (nfft < 2 * n_t) nfft <<= 1;                     // 2 * next power of two >= n_t, as emcee pads
     const int Mh = nfft / 2 + 1;
-    cudaStream_t st = nullptr;
-    MTG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    double *d_x = nullptr, *d_pad = nullptr, *d_out = nullptr; double2 *d_spec = nullptr;
-    cufftHandle fwd = 0, inv = 0;
+    AcfCtx &c = g_acf;
+    std::lock_guard<std::mutex> lock(c.mu);
+    int dev = 0;
+    MTG_CUDA(cudaGetDevice(&dev));
+    if (dev != c.device) { c.drop_all(); c.device = dev; }
+    if (!c.st) MTG_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
     int rc = 0;
-    if (cudaMalloc((void **)&d_x, sizeof(double) * (size_t)L * n_t) != cudaSuccess ||
-        cudaMalloc((void **)&d_pad, sizeof(double) * (size_t)L * nfft) != cudaSuccess ||
-        cudaMalloc((void **)&d_spec, sizeof(double2) * (size_t)L * Mh) != cudaSuccess ||
-        cudaMalloc((void **)&d_out, sizeof(double) * (size_t)L * n_t) != cudaSuccess) { mtg_set_error("mtg_autocorr_host: out of memory"); rc = MTG_ENOMEM; }
-    int nn[1] = {nfft};
-    if (!rc && (cufftPlanMany(&fwd, 1, nn, nullptr, 1, nfft, nullptr, 1, Mh, CUFFT_D2Z, L) != CUFFT_SUCCESS ||
-                cufftPlanMany(&inv, 1, nn, nullptr, 1, Mh, nullptr, 1, nfft, CUFFT_Z2D, L) != CUFFT_SUCCESS)) {
-        mtg_set_error("mtg_autocorr_host: cufftPlanMany(n=%d, batch=%d) failed", nfft, L); rc = MTG_ENOMEM;
+    if ((rc = acf_grow((void **)&c.d_out, &c.cap_out, sizeof(double) * (size_t)L * n_t)) ||
+        (rc = acf_grow((void **)&c.d_x, &c.cap_x, sizeof(double) * (size_t)L * n_t)) ||
+        (rc = acf_grow((void **)&c.d_pad, &c.cap_pad, sizeof(double) * (size_t)L * nfft)) ||
+        (rc = acf_grow((void **)&c.d_spec, &c.cap_spec, sizeof(double2) * (size_t)L * Mh))) return rc;
+    if (nfft != c.nfft || L != c.L) {
+        c.drop_plans();
+        int nn[1] = {nfft};
+        if (cufftPlanMany(&c.fwd, 1, nn, nullptr, 1, nfft, nullptr, 1, Mh, CUFFT_D2Z, L) != CUFFT_SUCCESS ||
+            cufftPlanMany(&c.inv, 1, nn, nullptr, 1, Mh, nullptr, 1, nfft, CUFFT_Z2D, L) != CUFFT_SUCCESS) {
+            c.drop_plans();
+            mtg_set_error("mtg_autocorr_host: cufftPlanMany(n=%d, batch=%d) failed", nfft, L); return MTG_ENOMEM;
+        }
+        cufftSetStream(c.fwd, c.st); cufftSetStream(c.inv, c.st);
+        c.nfft = nfft; c.L = L;
     }
-    if (!rc) {
-        cufftSetStream(fwd, st); cufftSetStream(inv, st);
-        cudaMemcpyAsync(d_x, x_rows, sizeof(double) * (size_t)L * n_t, cudaMemcpyHostToDevice, st);
-        k_acf_center_pad<<<L, 256, 0, st>>>(n_t, nfft, d_x, d_pad);
-        if (cufftExecD2Z(fwd, d_pad, (cufftDoubleComplex *)d_spec) != CUFFT_SUCCESS) { mtg_set_error("cufftExecD2Z failed"); rc = MTG_EINVAL; }
-    }
-    if (!rc) {
-        const size_t tot = (size_t)L * Mh;
-        k_acf_power<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, d_spec);
-        if (cufftExecZ2D(inv, (cufftDoubleComplex *)d_spec, d_pad) != CUFFT_SUCCESS) { mtg_set_error("cufftExecZ2D failed"); rc = MTG_EINVAL; }
-    }
-    if (!rc) {
-        k_acf_normalise<<<dim3((n_t + 255) / 256, L), 256, 0, st>>>(n_t, nfft, d_pad, d_out);
-        mtg_count_launch(3);
-        cudaMemcpyAsync(out_acf, d_out, sizeof(double) * (size_t)L * n_t, cudaMemcpyDeviceToHost, st);
-        rc = mtg_cuda_check(cudaStreamSynchronize(st), "mtg_autocorr_host sync");
-    }
-    if (fwd) cufftDestroy(fwd);
-    if (inv) cufftDestroy(inv);
-    cudaFree(d_x); cudaFree(d_pad); cudaFree(d_spec); cudaFree(d_out);
-    cudaStreamDestroy(st);
-    return rc;
+    cudaStream_t st = c.st;
+    cudaMemcpyAsync(c.d_x, x_rows, sizeof(double) * (size_t)L * n_t, cudaMemcpyHostToDevice, st);
+    k_acf_center_pad<<<L, 256, 0, st>>>(n_t, nfft, c.d_x, c.d_pad);
+    if (cufftExecD2Z(c.fwd, c.d_pad, (cufftDoubleComplex *)c.d_spec) != CUFFT_SUCCESS) { mtg_set_error("cufftExecD2Z failed"); return MTG_EINVAL; }
+    const size_t tot = (size_t)L * Mh;
+    k_acf_power<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, c.d_spec);
+    if (cufftExecZ2D(c.inv, (cufftDoubleComplex *)c.d_spec, c.d_pad) != CUFFT_SUCCESS) { mtg_set_error("cufftExecZ2D failed"); return MTG_EINVAL; }
+    k_acf_normalise<<<dim3((n_t + 255) / 256, L), 256, 0, st>>>(n_t, nfft, c.d_pad, c.d_out);
+    mtg_count_launch(3);
+    cudaMemcpyAsync(out_acf, c.d_out, sizeof(double) * (size_t)L * n_t, cudaMemcpyDeviceToHost, st);
+    return mtg_cuda_check(cudaStreamSynchronize(st), "mtg_autocorr_host sync");
 }
