@@ -299,3 +299,12 @@ class GPModelling(object):
         noisy, dy = simulator.add_noise(rates)
         simulator.close()
         return [GappyLightcurve(self._lightcurve.times, noisy[i], dy[i]) for i in range(nsims)]
+
+    def _generate_lc_from_params(self, parameters, simulator):
+        """One lightcurve from one parameter vector with ``simulator`` (gpmodelling.py:516-539): the unit of work the
+        reference maps over a process pool; ``generate_from_posteriors`` above does all of them in one batched call."""
+        self.gp.set_parameter_vector(parameters)
+        simulator.psd_model = self.gp.kernel.get_psd
+        rates = simulator.generate_lightcurve()
+        noisy_rates, dy = simulator.add_noise(rates)
+        return GappyLightcurve(self._lightcurve.times, noisy_rates, dy)

@@ -201,3 +201,27 @@ def test_finite_difference_steps_follow_scipy_at_the_bounds():
     mine = np.array([(f(x + np.eye(5)[k] * ((x + np.eye(5)[k] * h[k])[k] - x[k])) - f(x)) / ((x + np.eye(5)[k] * h[k])[k] - x[k]) for k in range(5)])
     ref = approx_derivative(f, x, method="2-point", abs_step=1e-8, bounds=(lo, hi))
     np.testing.assert_allclose(mine[[0, 1, 3]], ref[[0, 1, 3]], rtol=1e-12)      # where the plain step fits, identical to scipy
+
+
+def test_generate_lc_from_params_plumbing():
+    """GPModelling._generate_lc_from_params (gpmodelling.py:516-539) with a stand-in simulator: parameters set on the GP,
+    the kernel's PSD handed to the simulator, rates -> noise -> GappyLightcurve on the input timestamps."""
+    bounds_drw = [(4.0, 6.0), (8.0, 12.0)]; bounds_lor = [(5, 15), (1, 6), (-7, -1)]
+    gpmodel = _gpmodel(bounds_drw, bounds_lor)
+
+    class FakeSimulator(object):
+        psd_model = None
+
+        def generate_lightcurve(self):
+            self.psd_at_call = self.psd_model(np.array([0.1, 1.0]))
+            return np.full(100, 2.0)
+
+        def add_noise(self, rates):
+            return rates + 0.5, np.full(len(rates), 0.25)
+
+    sim = FakeSimulator()
+    params = np.array([4.5, 9.0, 9.0, 2.0, -3.0])
+    lc = gpmodel._generate_lc_from_params(params, sim)
+    np.testing.assert_array_equal(gpmodel.gp.get_parameter_vector(), params)
+    np.testing.assert_allclose(sim.psd_at_call, gpmodel.gp.kernel.get_psd(np.array([0.1, 1.0])))
+    assert np.all(lc.y == 2.5) and np.all(lc.dy == 0.25) and np.array_equal(lc.times, np.arange(100))
