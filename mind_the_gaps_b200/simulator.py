@@ -23,7 +23,7 @@ from .lightcurves.regular import Lightcurve
 from .noise_models import GaussianNoise, KraftNoise, PoissonNoise
 from .stats import create_log_normal, create_uniform_distribution
 
-__all__ = ["Simulator", "TK95Simulator", "E13Simulator", "get_fft", "cut_random_segment", "get_segment"]
+__all__ = ["Simulator", "TK95Simulator", "E13Simulator", "add_poisson_noise", "get_fft", "cut_random_segment", "get_segment"]
 
 
 class BaseSimulatorMethod(object):
@@ -326,6 +326,20 @@ class Simulator(object):
         if "seed" not in inject:
             inject["seed"] = self._seed()
         return self.noise.add_noise(rates, **inject)
+
+
+def add_poisson_noise(rates, exposures, background_counts=None, bkg_rate_err=None):
+    """Legacy module-level helper of the reference (simulator.py:423-465): Poisson-distributed total counts drawn with
+    ``np.random.poisson`` on the host (so a seeded NumPy run reproduces the reference's numbers), net rates and their
+    uncertainties.  ``Simulator.add_noise`` / ``noise_models.PoissonNoise`` are the device path."""
+    rates = np.asarray(rates, dtype=np.float64)
+    if background_counts is None:
+        background_counts = np.zeros(len(rates), dtype=int)
+    if bkg_rate_err is None:
+        bkg_rate_err = np.zeros(len(rates), dtype=int)
+    drawn = np.random.poisson(rates * exposures + background_counts)
+    dy = np.sqrt((np.sqrt(drawn) / exposures) ** 2 + np.asarray(bkg_rate_err) ** 2)
+    return (drawn - background_counts) / exposures, dy
 
 
 def get_fft(N, dt, model, real=None, im=None):

@@ -11,7 +11,8 @@ import numpy as np
 from scipy import special, stats
 from scipy.stats import lognorm, uniform
 
-__all__ = ["kraft_pdf", "lognormal", "chi_cov", "chi_log_likehood", "chi_square", "create_log_normal",
+__all__ = ["kraft_pdf", "lognormal", "chi_cov", "chi_log_likehood", "chi_log_likehood_nonyq", "chi_square", "chi_square_N", "fit_N",
+           "neg_log_like", "create_log_normal",
            "create_uniform_distribution", "aic", "aicc", "bic", "lrt_statistic", "lrt_pvalue", "lrt_summary"]
 
 
@@ -56,15 +57,42 @@ def chi_cov(powers_data, model_powers=None, inv_cov=None):
     return np.matmul(np.matmul(d, inv_cov), d.T)
 
 
-def chi_log_likehood(powers_data, model_pows=None, nyquist=False):
-    if nyquist:
-        ll = 2. * np.sum(np.log(model_pows[:-1]) + powers_data[:-1] / model_pows[:-1])
-        return ll + np.log(np.pi * powers_data[-1] * model_pows[-1]) + 2 * powers_data[-1] / model_pows[-1]
+def chi_log_likehood_nonyq(powers_data, model_pows=None):
+    """Whittle statistic of Vaughan+2005 eq. A.3 / Emmanoulopoulos+2013 A.11 for chi^2_2-distributed powers (stats.py:81-91)."""
     return 2. * np.sum(np.log(model_pows) + powers_data / model_pows)
+
+
+def chi_log_likehood(powers_data, model_pows=None, nyquist=False):
+    """The same with the last (Nyquist, chi^2_1-distributed) power treated apart when ``nyquist`` (stats.py:59-78)."""
+    if nyquist:
+        ll = chi_log_likehood_nonyq(powers_data[:-1], model_pows[:-1])
+        return ll + np.log(np.pi * powers_data[-1] * model_pows[-1]) + 2 * powers_data[-1] / model_pows[-1]
+    return chi_log_likehood_nonyq(powers_data, model_pows)
 
 
 def chi_square(powers_data, model_powers=None, sigmas=None):
     return np.sum(((model_powers - powers_data) / sigmas) ** 2)
+
+
+def fit_N(loglikehood, log_like_args=()):
+    """Normalisation minimising ``loglikehood(N, *log_like_args)`` (BFGS from 1; stats.py:31-41)."""
+    from scipy.optimize import minimize
+    return minimize(loglikehood, 1, args=log_like_args, method="BFGS").x
+
+
+def chi_square_N(powers_data, model_power=None, std_power=None):
+    """``chi_square`` at the best-fitting normalisation of the model (the reference's version, stats.py:108-113, passes the
+    normalisation as an extra leading argument that ``chi_square`` does not take and cannot run; here the normalisation
+    scales the model powers)."""
+    scaled = lambda N, p, m, s: chi_square(p, np.ravel(N)[0] * m, s)
+    N = fit_N(scaled, (powers_data, model_power, std_power))
+    return scaled(N, powers_data, model_power, std_power)
+
+
+def neg_log_like(params, y, gp):
+    """``-gp.log_likelihood(y)`` at ``params`` (stats.py:149-152)."""
+    gp.set_parameter_vector(params)
+    return -gp.log_likelihood(y)
 
 
 def bic(loglikehood, n, k):

@@ -225,3 +225,29 @@ def test_generate_lc_from_params_plumbing():
     np.testing.assert_array_equal(gpmodel.gp.get_parameter_vector(), params)
     np.testing.assert_allclose(sim.psd_at_call, gpmodel.gp.kernel.get_psd(np.array([0.1, 1.0])))
     assert np.all(lc.y == 2.5) and np.all(lc.dy == 0.25) and np.array_equal(lc.times, np.arange(100))
+
+
+def test_small_reference_helpers():
+    """stats.chi_log_likehood(_nonyq), fit_N / chi_square_N and simulator.add_poisson_noise (stats.py:31-113,
+    simulator.py:423-465)."""
+    from mind_the_gaps_b200 import stats as st
+    from mind_the_gaps_b200.simulator import add_poisson_noise
+    rng = np.random.default_rng(0)
+    model = 3.0 * np.linspace(0.01, 0.5, 50) ** -1.0
+    powers = model * rng.exponential(1.0, 50)
+    s = st.chi_log_likehood_nonyq(powers, model)
+    assert s == 2.0 * np.sum(np.log(model) + powers / model) == st.chi_log_likehood(powers, model)
+    with_nyq = st.chi_log_likehood(powers, model, nyquist=True)
+    assert abs(with_nyq - (st.chi_log_likehood_nonyq(powers[:-1], model[:-1]) + np.log(np.pi * powers[-1] * model[-1]) + 2 * powers[-1] / model[-1])) < 1e-12
+    # best-fitting normalisation of a model that is off by a factor 2.5
+    data = 2.5 * model
+    assert abs(st.fit_N(lambda N, p, m, sg: st.chi_square(p, np.ravel(N)[0] * m, sg), (data, model, np.ones(50)))[0] - 2.5) < 1e-4
+    assert st.chi_square_N(data, model, np.ones(50)) < 1e-6
+    np.random.seed(4)
+    rates, dy = add_poisson_noise(np.full(2000, 0.5), 1000.0)
+    np.random.seed(4)
+    counts = np.random.poisson(np.full(2000, 500.0))
+    np.testing.assert_array_equal(rates, counts / 1000.0)
+    np.testing.assert_array_equal(dy, np.sqrt(counts) / 1000.0)
+    rates_b, dy_b = add_poisson_noise(np.full(10, 0.5), 1000.0, background_counts=np.full(10, 20), bkg_rate_err=np.full(10, 0.001))
+    assert np.all(dy_b > 0) and abs(np.mean(rates_b) - 0.5) < 0.1
