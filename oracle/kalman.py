@@ -8,25 +8,28 @@ TEST INFRASTRUCTURE ONLY -- the NumPy statement of what ``csrc/mtg_scan.cu`` (ke
 * ``loglike_sequential``: prediction-error decomposition (the classical filter).
 * ``loglike_scan``: the same filter as a prefix sum over the associative operator of Sarkka & Garcia-Fernandez (IEEE TAC
   2021) with the chunk / scan / re-filter structure of the kernel.
-Both equal ``oracle.gp.loglike_dense`` to rounding (tests/test_oracle.py)."""
+Both equal ``oracle.gp.loglike_dense`` to rounding (tests/test_oracle.py).  Every function is analytic in the coefficients and
+works in ``complex128``, so ``grad_complex_step_scan`` differentiates THROUGH the scan: forward-mode derivatives survive the
+operator (inverse included) to rounding -- the groundwork for a scan-based gradient kernel."""
 import numpy as np
 
 
 def statespace(ar, cr, ac, bc, cc, dc):
-    blocks = [("r", a, c) for a, c in zip(ar, cr) if a != 0.0] + [("c", a, b, c, d) for a, b, c, d in zip(ac, bc, cc, dc)]
+    blocks = [("r", a, c) for a, c in zip(ar, cr) if np.real(a) != 0.0] + [("c", a, b, c, d) for a, b, c, d in zip(ac, bc, cc, dc)]
     J = sum(1 if bl[0] == "r" else 2 for bl in blocks)
-    Pinf = np.zeros((J, J)); h = np.zeros(J)
+    dt_ = np.result_type(*[np.asarray(v).dtype for bl in blocks for v in bl[1:]], np.float64)      # complex for complex-step derivatives
+    Pinf = np.zeros((J, J), dtype=dt_); h = np.zeros(J)
     i = 0
     for bl in blocks:
         if bl[0] == "r":
             Pinf[i, i] = bl[1]; h[i] = 1.0; i += 1
         else:
             _, a, b, c, d = bl
-            p22 = a if b == 0.0 else a + 2.0 * c * b / d
+            p22 = a if np.real(b) == 0.0 and np.imag(b) == 0.0 else a + 2.0 * c * b / d
             Pinf[i:i + 2, i:i + 2] = [[a, b], [b, p22]]; h[i] = 1.0; i += 2
 
     def transition(dt):
-        F = np.zeros((J, J)); i = 0
+        F = np.zeros((J, J), dtype=dt_); i = 0
         for bl in blocks:
             if bl[0] == "r":
                 F[i, i] = np.exp(-bl[2] * dt); i += 1
@@ -47,7 +50,7 @@ def _step(m, P, F, Pinf, h, y, R):
 
 def loglike_sequential(t, resid, diag, model):
     J, Pinf, h, transition = model
-    m, P, ll = np.zeros(J), Pinf.copy(), 0.0
+    m, P, ll = np.zeros(J, dtype=Pinf.dtype), Pinf.copy(), 0.0
     for n in range(len(t)):
         F = transition(t[n] - t[n - 1]) if n else np.eye(J)
         m, P, l = _step(m, P, F, Pinf, h, resid[n], diag[n])
@@ -79,10 +82,11 @@ def loglike_scan(t, resid, diag, model, threads=256):
     N = len(t)
     ch = -(-N // threads)
     bounds = [(min(k * ch, N), min(k * ch + ch, N)) for k in range(threads)]
-    ident = lambda: (np.eye(J), np.zeros(J), np.zeros((J, J)), np.zeros(J), np.zeros((J, J)))
+    cd = Pinf.dtype
+    ident = lambda: (np.eye(J, dtype=cd), np.zeros(J, dtype=cd), np.zeros((J, J), dtype=cd), np.zeros(J, dtype=cd), np.zeros((J, J), dtype=cd))
     comps = []
     for k, (n0, n1) in enumerate(bounds):                       # phase 1
-        e = (np.zeros((J, J)), np.zeros(J), Pinf.copy(), np.zeros(J), np.zeros((J, J))) if k == 0 else ident()
+        e = (np.zeros((J, J), dtype=cd), np.zeros(J, dtype=cd), Pinf.copy(), np.zeros(J, dtype=cd), np.zeros((J, J), dtype=cd)) if k == 0 else ident()
         for n in range(n0, n1):
             F = transition(t[n] - t[n - 1]) if n else np.eye(J)
             e = _append(e, F, Pinf, h, resid[n], diag[n])
@@ -93,9 +97,23 @@ def loglike_scan(t, resid, diag, model, threads=256):
         d *= 2
     ll = 0.0
     for k, (n0, n1) in enumerate(bounds):                       # phase 3
-        m, P = (np.zeros(J), Pinf.copy()) if k == 0 else (pref[k - 1][1], pref[k - 1][2])
+        m, P = (np.zeros(J, dtype=cd), Pinf.copy()) if k == 0 else (pref[k - 1][1], pref[k - 1][2])
         for n in range(n0, n1):
             F = transition(t[n] - t[n - 1]) if n else np.eye(J)
             m, P, l = _step(m, P, F, Pinf, h, resid[n], diag[n])
             ll += l
     return ll
+
+
+def grad_complex_step_scan(spec, params, t, resid, diag, h=1e-30, threads=64):
+    """d loglike / d params by complex-step differentiation through ``loglike_scan`` (one evaluation per parameter)."""
+    from . import terms as _terms
+    params = np.asarray(params, dtype=float)
+    g = np.empty(len(params))
+    for k in range(len(params)):
+        p = params.astype(complex); p[k] += 1j * h
+        co = _terms.coefficients(spec, p)
+        ar, cr, ac, bc, cc, dc = [np.atleast_1d(np.asarray(x)) for x in co[:6]]
+        jit = co[6] if len(co) > 6 else 0.0
+        g[k] = np.imag(loglike_scan(t, resid, diag + jit, statespace(ar, cr, ac, bc, cc, dc), threads=threads)) / h
+    return g
