@@ -35,6 +35,18 @@ class LRTResult(object):
     def pvalue(self, T_obs):
         return lrt_pvalue(self.T, T_obs)
 
+    _FIELDS = ("T", "loglike_null", "loglike_alt", "params_null", "params_alt", "status_null", "status_alt")
+
+    def save(self, path):
+        """Write the arrays of the test to ``path`` (``.npz``): the reference's workflow keeps such per-run result files
+        (``docs/workflow.md:44-45, 77, 92``: ``fits_results.dat``) so that the 10^4 simulations need not be redone."""
+        np.savez_compressed(path, **{k: np.asarray(getattr(self, k)) for k in self._FIELDS})
+
+    @classmethod
+    def load(cls, path):
+        with np.load(path) as z:
+            return cls(*[z[k] for k in cls._FIELDS])
+
 
 def shard_range(n, rank, world):
     """Contiguous block of ``n`` items owned by ``rank`` (sizes differ by at most one)."""

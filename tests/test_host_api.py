@@ -251,3 +251,16 @@ def test_small_reference_helpers():
     np.testing.assert_array_equal(dy, np.sqrt(counts) / 1000.0)
     rates_b, dy_b = add_poisson_noise(np.full(10, 0.5), 1000.0, background_counts=np.full(10, 20), bkg_rate_err=np.full(10, 0.001))
     assert np.all(dy_b > 0) and abs(np.mean(rates_b) - 0.5) < 0.1
+
+
+def test_lrt_result_round_trip(tmp_path):
+    from mind_the_gaps_b200.lrt import LRTResult
+    rng = np.random.default_rng(0)
+    res = LRTResult(rng.chisquare(3, 50), rng.normal(size=50), rng.normal(size=50), rng.normal(size=(50, 2)), rng.normal(size=(50, 5)),
+                    np.zeros(50, dtype=np.int32), np.ones(50, dtype=np.int32))
+    path = str(tmp_path / "lrt.npz")
+    res.save(path)
+    back = LRTResult.load(path)
+    for k in LRTResult._FIELDS:
+        np.testing.assert_array_equal(getattr(back, k), getattr(res, k))
+    assert back.pvalue(5.0) == res.pvalue(5.0)
