@@ -186,10 +186,38 @@ class GP(ModelSet):
         _native.check(rc)
         return (ll, grad, status) if return_status else (ll, grad)
 
+    def device_prior_supported(self):
+        """True when the device restates this model's ``log_prior`` exactly: the box of every parameter plus the two
+        overrides the kernels know (``ComplexTerm`` with ``log_b``: ``a c >= b d``; ``BendingPowerlaw``:
+        ``log_S0 >= log_Q``, celerite_models.py:85-90).  A user subclass that overrides ``log_prior`` -- even one that
+        inherits a device coefficient map -- makes this False, and the prior is then evaluated on the host."""
+        from ..models.celerite_models import BendingPowerlaw
+        from .terms import ComplexTerm, TermSum
+        known = {Model.log_prior, ModelSet.log_prior, TermSum.log_prior, ComplexTerm.log_prior, BendingPowerlaw.log_prior}
+        parts = list(self.kernel.terms) + [self.kernel, self.mean]
+        return all(type(m).log_prior in known for m in parts)
+
     def log_probability_batch(self, y, params, kernel="auto"):
         """``log_prior + log_likelihood`` for B parameter vectors: ``GPModelling._log_probability``
         (gpmodelling.py:127-152) vectorised; ``-inf`` outside the prior or when not positive definite."""
-        return self.log_likelihood_batch(y, params, apply_prior=True, kernel=kernel)
+        if self.device_prior_supported():
+            return self.log_likelihood_batch(y, params, apply_prior=True, kernel=kernel)
+        # a log_prior the device does not know: the prior row by row on the host (arbitrary Python, as the reference
+        # runs it), the likelihood of the rows inside it in one launch
+        p = self._batch_params(params)
+        keep = self.get_parameter_vector()
+        lp = np.empty(p.shape[0])
+        try:
+            for i, row in enumerate(p):
+                self.set_parameter_vector(row)
+                lp[i] = self.log_prior()
+        finally:
+            self.set_parameter_vector(keep)
+        out = np.full(p.shape[0], -np.inf)
+        ok = np.isfinite(lp)
+        if np.any(ok):
+            out[ok] = lp[ok] + self.log_likelihood_batch(y, p[ok], apply_prior=False, kernel=kernel)
+        return out
 
     # -- celerite single-point API ---------------------------------------------------------------------
     def log_likelihood(self, y, _const=None, quiet=False):

@@ -131,8 +131,10 @@ extern "C" int mtg_model_width(const mtg_model_t *model, int *j_celerite, int *j
 }
 
 // ---- host-buffer context ----------------------------------------------------------------------
-// One lazily created context per (process, device): an internal stream and grow-only device
-// buffers, so repeated host calls (an emcee loop) do not pay cudaMalloc each time.
+// One lazily created context per (process, DEVICE): an internal stream, a small chunk pipeline and grow-only device
+// buffers, all created on that device, so repeated host calls (an emcee loop) do not pay cudaMalloc each time and one
+// process can drive several GPUs (mtg_set_device(d) then mtg_*_host).  The mutex is per context: host calls aimed
+// at different devices run concurrently, calls aimed at the same device share its buffers and serialise.
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     int reserve(size_t bytes)
@@ -152,20 +154,25 @@ struct HostCtx {
     cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};      // chunk pipeline of large host calls
     cudaEvent_t data_ready = nullptr;
     DevBuf t, y, d, ysn, dsn, mean, par, ll, grad, st, x, nll, it, scratch;
-    int ensure()
+    int ensure(int dev)          // called with mu held and `dev` current
     {
-        int dev = 0;
-        MTG_CUDA(cudaGetDevice(&dev));
-        if (stream && dev == device) return 0;
-        if (!stream) {
-            MTG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-            for (int i = 0; i < NPIPE; ++i) MTG_CUDA(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
-            MTG_CUDA(cudaEventCreateWithFlags(&data_ready, cudaEventDisableTiming));
-        }
+        if (stream) return 0;
+        MTG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < NPIPE; ++i) MTG_CUDA(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
+        MTG_CUDA(cudaEventCreateWithFlags(&data_ready, cudaEventDisableTiming));
         device = dev; return 0;
     }
 };
-static HostCtx g_ctx;
+#define MTG_MAX_DEVICES 64
+static HostCtx g_ctx[MTG_MAX_DEVICES];
+// the context of the calling thread's current device (NULL + error text when there is none)
+static HostCtx *host_ctx()
+{
+    int dev = -1;
+    if (mtg_cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    if (dev < 0 || dev >= MTG_MAX_DEVICES) { mtg_set_error("device index %d out of range", dev); return nullptr; }
+    return &g_ctx[dev];
+}
 
 __global__ void k_transpose_sn_to_ns(const double *__restrict__ in, double *__restrict__ out, int S, int N)
 {
@@ -232,9 +239,11 @@ static int host_eval(const mtg_model_t *model, int N, int S, int group, int B,
         mtg_set_error("mtg_loglike_host: bad argument"); return MTG_EINVAL;
     }
     if (B == 0) return 0;
-    HostCtx &c = g_ctx;
+    HostCtx *cp = host_ctx();
+    if (!cp) return MTG_ENODEV;
+    HostCtx &c = *cp;
     std::lock_guard<std::mutex> lock(c.mu);
-    int rc = c.ensure();
+    int rc = c.ensure((int)(cp - g_ctx));
     if (rc) return rc;
     const int nd = model->n_free;
     if ((rc = upload_data(c, N, S, t, y_sn, diag_sn, ds_mean, flags))) return rc;
@@ -311,9 +320,11 @@ extern "C" int mtg_lbfgs_host(const mtg_model_t *model, int N, int S, int group,
         mtg_set_error("mtg_lbfgs_host: bad argument"); return MTG_EINVAL;
     }
     if (B == 0) return 0;
-    HostCtx &c = g_ctx;
+    HostCtx *cp = host_ctx();
+    if (!cp) return MTG_ENODEV;
+    HostCtx &c = *cp;
     std::lock_guard<std::mutex> lock(c.mu);
-    int rc = c.ensure();
+    int rc = c.ensure((int)(cp - g_ctx));
     if (rc) return rc;
     const int nd = model->n_free;
     if (nd < 1) { mtg_set_error("mtg_lbfgs_host: no free parameters"); return MTG_EINVAL; }

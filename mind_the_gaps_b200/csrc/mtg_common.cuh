@@ -62,8 +62,9 @@ __device__ __forceinline__ double plan_param(const Plan &pl, const double *__res
     return pos >= 0 ? x[pos] : pl.full_default[i];
 }
 
-// celerite Model.log_prior: 0 inside the closed box else -inf; BendingPowerlaw override
-// (celerite_models.py:85-90).  Returns true when inside.
+// celerite Model.log_prior: 0 inside the closed box else -inf; the overrides the reference path can reach:
+// BendingPowerlaw (celerite_models.py:85-90) and celerite's ComplexTerm with four parameters.  Returns true when inside.
+// (Any other log_prior override is detected on the host, GP.device_prior_supported, and evaluated there.)
 __device__ __forceinline__ bool plan_in_prior(const Plan &pl, const double *__restrict__ x)
 {
     bool ok = true;
@@ -73,6 +74,12 @@ __device__ __forceinline__ bool plan_in_prior(const Plan &pl, const double *__re
     }
     for (int k = 0; k < pl.n_bpl; ++k)
         ok = ok && !(plan_param(pl, x, pl.bpl_s0[k]) < plan_param(pl, x, pl.bpl_q[k]));
+    // celerite ComplexTerm.log_prior with a fitted log_b: -inf when a c < b d (the term is then not positive definite)
+    for (int j = 0; j < pl.jc; ++j)
+        if (pl.c_kind[j] == CS_COMPLEX4) {
+            const int *ix = pl.c_idx[j];
+            ok = ok && !(plan_param(pl, x, ix[0]) + plan_param(pl, x, ix[2]) < plan_param(pl, x, ix[1]) + plan_param(pl, x, ix[3]));
+        }
     return ok;
 }
 

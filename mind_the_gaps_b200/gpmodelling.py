@@ -132,6 +132,9 @@ class GPModelling(object):
         old_tau = np.inf
         self.converged = False
         y = self._lightcurve.y
+        if device_sampler and not self.gp.device_prior_supported():
+            warnings.warn("a kernel term overrides log_prior: sampling with the host loop (prior on the host, likelihood batches on the device)")
+            device_sampler = False
         if device_sampler:
             # the whole stretch-move loop on the GPU (kernel K8), one launch per convergence interval
             sampler = DeviceEnsembleSampler(walkers, self.gp, y, block=every_samples)

@@ -22,7 +22,7 @@ from . import _native
 from .celerite import GP
 from .stats import lrt_pvalue, lrt_statistic
 
-__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts", "all_gather_rows", "all_gather_varlen"]
+__all__ = ["LRTResult", "simulate_and_fit", "shard_range", "alternative_starts", "infer_null_slots", "all_gather_rows", "all_gather_varlen"]
 
 
 class LRTResult(object):
@@ -32,8 +32,22 @@ class LRTResult(object):
         self.status_null = status_null; self.status_alt = status_alt
         self.timings = timings or {}
 
-    def pvalue(self, T_obs):
-        return lrt_pvalue(self.T, T_obs)
+    @property
+    def n_used(self):
+        """Number of simulations with a finite statistic, i.e. what ``pvalue`` is computed from."""
+        return int(np.count_nonzero(np.isfinite(self.T)))
+
+    @property
+    def n_invalid(self):
+        """Simulations discarded because the noise model could not be applied (negative expected counts: the reference's
+        ``np.random.poisson`` raises ``ValueError("lam < 0")`` there, noise_models.py:72) or because a fit failed."""
+        return int(len(self.T) - self.n_used)
+
+    def pvalue(self, T_obs, return_n=False):
+        """``1 - percentileofscore(T_dist, T_obs) / 100`` over the ``n_used`` finite statistics;
+        ``return_n=True`` returns ``(p, n_used)``."""
+        p = lrt_pvalue(self.T, T_obs)
+        return (p, self.n_used) if return_n else p
 
     _FIELDS = ("T", "loglike_null", "loglike_alt", "params_null", "params_alt", "status_null", "status_alt")
 
@@ -106,6 +120,34 @@ def _bounds_arrays(gp):
     lo = np.array([-np.inf if x[0] is None else x[0] for x in b], dtype=np.float64)
     hi = np.array([np.inf if x[1] is None else x[1] for x in b], dtype=np.float64)
     return lo, hi
+
+
+def _term_signature(term):
+    """What makes two kernel terms "the same component" for nesting: class, parameter names and frozen mask."""
+    return (type(term), tuple(term.get_parameter_names(include_frozen=True)), tuple(bool(m) for m in np.atleast_1d(term.unfrozen_mask)))
+
+
+def infer_null_slots(null_kernel, alt_kernel):
+    """Positions, in the alternative kernel's free-parameter vector, of the parameters it shares with the null kernel.
+
+    The match is on TERM STRUCTURE (class, parameter names, frozen mask of every term), not on parameter names: the
+    null kernel's term list must appear as a contiguous run of the alternative's (``alt = extra + null`` as in the
+    reference's tutorial, ``ComplexTerm + RealTerm`` vs ``RealTerm``, docs/notebooks/tutorial_ppp.ipynb cells 7/9, or
+    ``alt = null + extra``).  Several matching runs (``alt = DRW + DRW``): the trailing one is taken when the
+    alternative ends with the null model, anything else is ambiguous.  No match or an ambiguous one raises
+    ``ValueError``: pass ``null_slots`` explicitly."""
+    t0 = [_term_signature(t) for t in null_kernel.terms]
+    t1 = [_term_signature(t) for t in alt_kernel.terms]
+    n0, n1 = len(t0), len(t1)
+    runs = [i for i in range(n1 - n0 + 1) if t1[i:i + n0] == t0]
+    if not runs:
+        raise ValueError("the null kernel's terms are not a contiguous run of the alternative's: pass null_slots explicitly")
+    if len(runs) > 1 and runs[-1] != n1 - n0:
+        raise ValueError("the null kernel matches the alternative's terms at positions %s: pass null_slots explicitly" % runs)
+    start = runs[-1]
+    free_per_term = [int(np.sum(np.atleast_1d(t.unfrozen_mask))) for t in alt_kernel.terms]
+    off = int(sum(free_per_term[:start]))
+    return list(range(off, off + int(sum(free_per_term[start:start + n0]))))
 
 
 def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
@@ -184,10 +226,10 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     nd0, nd1 = m0.n_free, m1.n_free
     lo0, hi0 = _bounds_arrays(gp0); lo1, hi1 = _bounds_arrays(gp1)
     if null_slots is None:
-        n0 = list(null_kernel.get_parameter_names()); n1 = list(alt_kernel.get_parameter_names())
-        strip = lambda s: s.split(":")[-1]
-        tail = [strip(s) for s in n1[len(n1) - nd0:]]; head = [strip(s) for s in n1[:nd0]]
-        null_slots = list(range(nd1 - nd0, nd1)) if tail == [strip(s) for s in n0] and head != tail else list(range(nd0))
+        null_slots = infer_null_slots(null_kernel, alt_kernel)
+    null_slots = [int(k) for k in null_slots]
+    if len(null_slots) != nd0 or len(set(null_slots)) != nd0 or min(null_slots) < 0 or max(null_slots) >= nd1:
+        raise ValueError("null_slots must name %d distinct positions of the alternative's %d free parameters" % (nd0, nd1))
     x_alt0 = gp1.get_parameter_vector().copy()
 
     N = lightcurve.n
@@ -202,14 +244,20 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     out_T = np.empty(L); out_l0 = np.empty(L); out_l1 = np.empty(L)
     out_p0 = np.empty((L, nd0)); out_p1 = np.empty((L, nd1)); out_s0 = np.empty(L, dtype=np.int32); out_s1 = np.empty(L, dtype=np.int32)
     kept = {}
-    times = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0}
+    times = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0, "n_invalid": 0}
     ev = lambda: torch.cuda.Event(enable_timing=True)
     main_stream = torch.cuda.current_stream(device)
 
     refine = int(refine_walkers) > 0 and int(refine_steps) > 0
+    if refine and not (gp0.device_prior_supported() and gp1.device_prior_supported()):
+        raise NotImplementedError("MCMC refinement runs on the device sampler, which does not restate a user-defined log_prior")
 
-    def mcmc_refine(model, nd, lo, hi, x_best, f_best, Lc, y, diag, means, rng, sp, purpose):
-        """max over a short ensemble run around ``x_best`` (Lc, nd); returns (loglike (Lc,), params (Lc, nd))"""
+    def mcmc_refine(model, nd, lo, hi, x_best, f_best, Lc, y, diag, means, rng, sp, purpose, first):
+        """max over a short ensemble run around ``x_best`` (Lc, nd); returns (loglike (Lc,), params (Lc, nd)).
+        ``first``: global index of the chunk's first simulation -- folded into the Philox key, because the counters only
+        carry the ensemble index INSIDE the launch and simulation k of every chunk / rank would otherwise see the same
+        split, stretch, partner and accept draws."""
+        ens_seed = (int(seed) * 7919 + purpose + 1000003 * (2 * int(first) + 1)) & 0xFFFFFFFFFFFFFFFF
         W = int(refine_walkers)
         std = np.abs(x_best) * 0.1
         p0 = x_best[:, None, :] + rng.normal(size=(Lc, W, nd)) * std[:, None, :]
@@ -219,7 +267,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         lpw = torch.empty((Lc, W), dtype=torch.float64, device=device)
         blp = torch.empty(Lc, dtype=torch.float64, device=device); bpos = torch.empty((Lc, nd), dtype=torch.float64, device=device)
         _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N, Lc, Lc, W, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(), means.data_ptr(),
-                                           pos.data_ptr(), lpw.data_ptr(), 1, int(refine_steps), 2.0, int(seed) * 7919 + purpose, 0,
+                                           pos.data_ptr(), lpw.data_ptr(), 1, int(refine_steps), 2.0, ens_seed, 0,
                                            None, None, None, blp.data_ptr(), bpos.data_ptr(), _native.FLAG_DS_MEAN, sp))
         b = blp.cpu().numpy(); bp = bpos.cpu().numpy()
         better = b > f_best
@@ -235,7 +283,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor,
                                        **(simulator_kwargs or {}))
         h = sim._sim()
-        local = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0}
+        local = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0, "n_invalid": 0}
         try:
             with torch.cuda.stream(stream):
                 for c0 in slot_chunks:
@@ -254,6 +302,10 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                                                             y.data_ptr(), dy.data_ptr(), sp))
                     _native.check(lib.mtg_prepare_data_dev(N, Lc, y.data_ptr(), dy.data_ptr(), diag.data_ptr(), means.data_ptr(), sp))
                     e1.record(stream)
+                    # negative expected counts (rate * exposure + background < 0: Gaussian-PDF simulations of faint / highly
+                    # variable sources) leave NaN in the lightcurve, hence in its mean; numpy raises ValueError("lam < 0")
+                    # for the reference (noise_models.py:72).  Such simulations are flagged (status 3, T = NaN), counted and reported.
+                    invalid = ~torch.isfinite(means)
                     # ---- null fits: start 0 = the generating parameters, others = 10 % Gaussian balls ------------
                     x0 = multistart_points(mine[c0:c0 + Lc], list(zip(lo0, hi0)), n_starts_null, rng)
                     B0 = Lc * n_starts_null
@@ -269,7 +321,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                     x_null = ox.cpu().numpy()[a0]
                     ll_null = -best0.cpu().numpy()
                     if refine:
-                        ll_null, x_null = mcmc_refine(m0, nd0, lo0, hi0, x_null, ll_null, Lc, y, diag, means, rng_ref, sp, 1)
+                        ll_null, x_null = mcmc_refine(m0, nd0, lo0, hi0, x_null, ll_null, Lc, y, diag, means, rng_ref, sp, 1, i0 + c0)
                     e2.record(stream)
                     # ---- alternative fits ---------------------------------------------------------------------------
                     x1 = alternative_starts(x_alt0, x_null, null_slots, lo1, hi1, n_starts_alt, rng).reshape(Lc * n_starts_alt, nd1)
@@ -286,14 +338,16 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
                     x_alt = ax.cpu().numpy()[a1]
                     ll_alt = -best1.cpu().numpy()
                     if refine:
-                        ll_alt, x_alt = mcmc_refine(m1, nd1, lo1, hi1, x_alt, ll_alt, Lc, y, diag, means, rng_ref, sp, 2)
+                        ll_alt, x_alt = mcmc_refine(m1, nd1, lo1, hi1, x_alt, ll_alt, Lc, y, diag, means, rng_ref, sp, 2, i0 + c0)
                     e3.record(stream)
                     stream.synchronize()
                     local["simulate_ms"] += e0.elapsed_time(e1); local["fit_null_ms"] += e1.elapsed_time(e2); local["fit_alt_ms"] += e2.elapsed_time(e3)
                     sl = slice(c0, c0 + Lc)
-                    out_l0[sl] = ll_null; out_l1[sl] = ll_alt
+                    inv = invalid.cpu().numpy()
+                    out_l0[sl] = np.where(inv, np.nan, ll_null); out_l1[sl] = np.where(inv, np.nan, ll_alt)
                     out_p0[sl] = x_null; out_p1[sl] = x_alt
-                    out_s0[sl] = os_.cpu().numpy()[a0]; out_s1[sl] = as_.cpu().numpy()[a1]
+                    out_s0[sl] = np.where(inv, 3, os_.cpu().numpy()[a0]); out_s1[sl] = np.where(inv, 3, as_.cpu().numpy()[a1])
+                    local["n_invalid"] += int(inv.sum())
                     if return_lightcurves:
                         kept[c0] = (y.cpu().numpy().T.copy(), dy.cpu().numpy().T.copy())
         finally:
@@ -312,6 +366,10 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         for k in times:
             times[k] += r[k]
     out_T[:] = lrt_statistic(out_l0, out_l1)
+    if times["n_invalid"]:
+        import warnings
+        warnings.warn("%d of %d simulated lightcurves had negative expected counts (the reference raises ValueError('lam < 0') "
+                      "there); they are excluded from the LRT distribution (status 3, T = NaN)" % (times["n_invalid"], L))
     timings = dict(times, n_local=L, chunk=chunk, pipeline=n_slots,
                    note="per-stage device times are summed over concurrently running chunks")
 

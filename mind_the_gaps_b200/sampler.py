@@ -202,6 +202,9 @@ class DeviceEnsembleSampler(EnsembleSampler):
     ``iteration`` advanced by the block; ``GPModelling.derive_posteriors`` sets it to its convergence interval)."""
 
     def __init__(self, nwalkers, gp, y, yerr=None, ensembles=1, a=2.0, seed=None, block=100, frozen_mean=None, kernel="auto"):
+        if not gp.device_prior_supported():
+            raise NotImplementedError("a kernel term overrides log_prior in a way the device sampler does not restate; "
+                                      "use the host sampler (derive_posteriors(device_sampler=False))")
         model = gp.device_model()
         if kernel not in ("auto", "k8", "scan"):
             raise ValueError("kernel must be 'auto', 'k8' or 'scan'")

@@ -264,3 +264,62 @@ def test_lrt_result_round_trip(tmp_path):
     for k in LRTResult._FIELDS:
         np.testing.assert_array_equal(getattr(back, k), getattr(res, k))
     assert back.pvalue(5.0) == res.pvalue(5.0)
+
+
+# ---- LRT nesting: the null model's slots inside the alternative's parameter vector (lrt.infer_null_slots) ----------
+def test_infer_null_slots_matches_term_structure_not_names():
+    from mind_the_gaps_b200 import lrt
+    from mind_the_gaps_b200.celerite import terms
+    from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+    # the reference tutorial's own models (tutorial_ppp.ipynb cells 7 / 9): the stripped names of the ComplexTerm's
+    # first two parameters equal the RealTerm's -- the match has to be on the term, not on the names
+    null = terms.RealTerm(0.0, 0.0)
+    alt = terms.ComplexTerm(0.0, 0.0, 0.0) + terms.RealTerm(0.0, 0.0)
+    assert lrt.infer_null_slots(null, alt) == [3, 4]
+    assert lrt.infer_null_slots(DampedRandomWalk(0.0, 0.0), Lorentzian(0.0, 1.0, 0.0) + DampedRandomWalk(0.0, 0.0)) == [3, 4]
+    assert lrt.infer_null_slots(DampedRandomWalk(0.0, 0.0), DampedRandomWalk(0.0, 0.0) + Lorentzian(0.0, 1.0, 0.0)) == [0, 1]
+    assert lrt.infer_null_slots(DampedRandomWalk(0.0, 0.0), DampedRandomWalk(0.0, 0.0) + DampedRandomWalk(0.0, 0.0)) == [2, 3]
+    # a frozen parameter in the leading term shifts the free-vector offsets
+    alt2 = terms.ComplexTerm(0.0, 0.0, 0.0) + terms.RealTerm(0.0, 0.0)
+    alt2.freeze_parameter("terms[0]:log_d")
+    assert lrt.infer_null_slots(null, alt2) == [2, 3]
+    with pytest.raises(ValueError):          # two interior matches: ambiguous
+        lrt.infer_null_slots(DampedRandomWalk(0.0, 0.0), DampedRandomWalk(0.0, 0.0) + DampedRandomWalk(0.0, 0.0) + Lorentzian(0.0, 1.0, 0.0))
+    with pytest.raises(ValueError):          # no structural match
+        lrt.infer_null_slots(terms.RealTerm(0.0, 0.0), Lorentzian(0.0, 1.0, 0.0) + DampedRandomWalk(0.0, 0.0))
+
+
+def test_alternative_starts_nest_the_null_optimum_for_tutorial_kernels():
+    from mind_the_gaps_b200 import lrt
+    from mind_the_gaps_b200.celerite import terms
+    null = terms.RealTerm(-1.0, -2.0)
+    alt = terms.ComplexTerm(-3.0, -4.0, -5.0, bounds=dict(log_a=(-10, 0), log_c=(-10, 0), log_d=(-10, 0))) + terms.RealTerm(-1.0, -2.0)
+    slots = lrt.infer_null_slots(null, alt)
+    x_null = np.array([[-1.5, -2.5], [-0.5, -1.0]])
+    lo = np.array([-10, -10, -10, -np.inf, -np.inf]); hi = np.array([0, 0, 0, np.inf, np.inf])
+    st = lrt.alternative_starts(alt.get_parameter_vector(), x_null, slots, lo, hi, 8, np.random.default_rng(0))
+    np.testing.assert_array_equal(st[:, 0, 3:], x_null)                  # start 0: null optimum in the RealTerm's slots
+    np.testing.assert_array_equal(st[:, 0, :3], np.tile([-3.0, -4.0, -5.0], (2, 1)))
+    np.testing.assert_array_equal(st[:, 5:, 3:], np.repeat(x_null[:, None, :], 3, axis=1))      # uniform starts keep the null part
+
+
+def test_device_prior_supported_flags_user_overrides():
+    from mind_the_gaps_b200.celerite import GP, terms
+    from mind_the_gaps_b200.models import BendingPowerlaw, DampedRandomWalk
+
+    class Strange(DampedRandomWalk):
+        def log_prior(self):
+            return -np.inf if self.log_S0 > 0 else super(Strange, self).log_prior()
+
+    assert GP(DampedRandomWalk(0.0, 0.0) + terms.ComplexTerm(0.0, -1.0, 0.0, 0.0)).device_prior_supported()
+    assert GP(BendingPowerlaw(0.0, -1.0, 0.0)).device_prior_supported()
+    assert not GP(Strange(0.0, 0.0) + DampedRandomWalk(0.0, 0.0)).device_prior_supported()
+
+
+def test_lrt_result_counts_used_simulations():
+    from mind_the_gaps_b200.lrt import LRTResult
+    T = np.array([1.0, 2.0, np.nan, 4.0])
+    r = LRTResult(T, T, T, np.zeros((4, 1)), np.zeros((4, 1)), np.zeros(4, int), np.array([0, 0, 3, 0]))
+    assert r.n_used == 3 and r.n_invalid == 1
+    p, n = r.pvalue(2.5, return_n=True)
+    assert n == 3 and abs(p - (1 - 2 / 3)) < 1e-12

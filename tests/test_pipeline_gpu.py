@@ -143,3 +143,80 @@ def test_tutorial_ppp_example_runs_end_to_end():
     assert 0.5 < np.median(out["T_dist"]) < 9 and 4 < np.percentile(out["T_dist"], 95) < 25
     out_q = mod.main(["--nsims", "200", "--max-steps", "3000", "--loop", "0", "--points", "400", "--qpo"])
     assert out_q["T_obs"] > np.percentile(out_q["T_dist"], 99) and out_q["p"] < 0.02
+
+
+def test_lrt_with_the_tutorial_realterm_complexterm_kernels_is_nested():
+    """tutorial_ppp.ipynb cells 7 / 9: null = RealTerm, alternative = ComplexTerm + RealTerm.  The stripped names of the
+    ComplexTerm's first parameters equal the RealTerm's; the nested start must still land in the RealTerm's slots."""
+    lc, truth = make_lc(200, 4)
+    null_kernel = terms.RealTerm(truth[0], truth[1], bounds=dict(log_a=(-15, 5), log_c=(-20, -5)))
+    alt_kernel = terms.ComplexTerm(truth[0] - 2, np.log(2 * np.pi / (10 * DAY) / 40.0), np.log(2 * np.pi / (10 * DAY)),
+                                   bounds=dict(log_a=(-20, 5), log_c=(-25, -8), log_d=(-16, -9))) + \
+        terms.RealTerm(truth[0], truth[1], bounds=dict(log_a=(-15, 5), log_c=(-20, -5)))
+    assert lrt.infer_null_slots(null_kernel, alt_kernel) == [3, 4]
+    samples = truth[None, :] + np.random.default_rng(5).normal(0, 0.15, (64, 2))
+    res = lrt.simulate_and_fit(lc, null_kernel, alt_kernel, samples, n_starts_null=2, n_starts_alt=6, seed=11)
+    assert np.all(np.isfinite(res.T)) and np.all(res.T > -1e-4)
+    assert res.n_used == 64 and res.n_invalid == 0
+
+
+def test_lrt_flags_simulations_with_negative_expected_counts():
+    """Gaussian-PDF simulation of a faint, highly variable source: some bins get rate * exposure < 0, where the reference's
+    np.random.poisson raises ValueError('lam < 0') (noise_models.py:72).  The device pipeline flags those simulations."""
+    lc, truth = make_lc(200, 4)
+    faint = GappyLightcurve(lc.times, lc.y * 0.2, lc.dy, lc.exposures)          # mean 0.1, sigma of the process 0.05..0.1
+    big = np.array([np.log(0.08 ** 2), truth[1]])
+    b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    null_kernel = DampedRandomWalk(big[0], big[1], bounds=b_drw)
+    alt_kernel = Lorentzian(big[0] - 2, np.log(20.0), np.log(2 * np.pi / (10 * DAY)),
+                            bounds=dict(log_S0=(-20, 5), log_Q=(0.5, 7), log_omega0=(-16, -9))) + DampedRandomWalk(big[0], big[1], bounds=b_drw)
+    samples = np.tile(big, (48, 1))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        res = lrt.simulate_and_fit(faint, null_kernel, alt_kernel, samples, n_starts_null=1, n_starts_alt=2, seed=2, max_iter=30)
+    assert res.n_invalid > 0 and res.n_used + res.n_invalid == 48
+    assert any("negative expected counts" in str(x.message) for x in w)
+    bad = ~np.isfinite(res.T)
+    assert np.all(res.status_null[bad] == 3) and np.all(res.status_alt[bad] == 3)
+    p, n = res.pvalue(3.0, return_n=True)
+    assert n == res.n_used and 0.0 <= p <= 1.0
+
+
+def test_complexterm_prior_is_applied_on_the_device():
+    """celerite ComplexTerm with a fitted log_b: log_prior = -inf when a c < b d.  The batched / sampler
+    log-probability must agree with GPModelling._log_probability row by row."""
+    lc, truth = make_lc(120, 6)
+    k = terms.ComplexTerm(truth[0], truth[0] - 1.0, truth[1], truth[1] + 1.0,
+                          bounds=dict(log_a=(-15, 5), log_b=(-15, 5), log_c=(-20, -5), log_d=(-20, -5))) + \
+        DampedRandomWalk(truth[0], truth[1], bounds=dict(log_S0=(-15, 5), log_omega0=(-20, -5)))
+    gpm = GPModelling(lc, k)
+    p0 = gpm.gp.get_parameter_vector()
+    rng = np.random.default_rng(1)
+    P = p0[None, :] + rng.normal(0, 1.5, (64, len(p0)))
+    batch = gpm._log_probability(P)
+    single = np.array([gpm._log_probability(row) for row in P])
+    viol = (P[:, 0] + P[:, 2]) < (P[:, 1] + P[:, 3])
+    assert viol.any() and (~viol).any()
+    assert np.all(np.isneginf(batch[viol]))
+    np.testing.assert_allclose(batch[~viol & np.isfinite(single)], single[~viol & np.isfinite(single)], rtol=1e-10)
+    assert np.array_equal(np.isfinite(batch), np.isfinite(single))
+
+
+def test_user_log_prior_override_is_evaluated_on_the_host():
+    lc, truth = make_lc(120, 6)
+
+    class Picky(DampedRandomWalk):              # inherits the device coefficient map, overrides the prior
+        def log_prior(self):
+            return -np.inf if self.log_S0 > -5.0 else super(Picky, self).log_prior()
+
+    gpm = GPModelling(lc, Picky(truth[0], truth[1], bounds=dict(log_S0=(-15, 5), log_omega0=(-20, -5))))
+    assert not gpm.gp.device_prior_supported()
+    P = np.array([[truth[0], truth[1]], [-4.0, truth[1]], [-6.0, truth[1]]])
+    out = gpm._log_probability(P)
+    assert np.isfinite(out[0]) == (truth[0] <= -5.0) and np.isneginf(out[1]) and np.isfinite(out[2])
+    np.testing.assert_allclose(out[2], gpm._log_probability(P[2]), rtol=1e-12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(0)
+        gpm.derive_posteriors(fit=False, max_steps=60, convergence_steps=30, walkers=8, progress=False)
+    assert np.all(gpm.mcmc_samples[:, 0] <= -5.0)
