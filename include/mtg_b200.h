@@ -289,6 +289,19 @@ int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
                       double *pos, double *lp, int init_lp, int nsteps, double a, uint64_t seed, uint64_t step0,
                       double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags);
 
+/* Test hook for sampler parity: the same run with the random draws of emcee 3.1.4 SUPPLIED by the caller instead of the
+ * Philox streams -- split[E][nsteps][W] = the shuffled `inds` of RedBlueMove.propose (0 / 1, ceil(W/2) zeros; walkers of a
+ * split are taken in ascending index order, as emcee does), and per step and half h, for the i-th walker of split h:
+ * uz = random.rand(Ns)[i] and rint = random.randint(Nc, size=Ns)[i] of StretchMove.get_proposal, uacc = the
+ * model.random.rand() of its accept test; all [E][nsteps][2][ceil(W/2)].  Proposal arithmetic is evaluated in emcee's
+ * order without FMA contraction, so the chain equals oracle/sampler.py's bit for bit (tests/test_ensemble_gpu.py).
+ * Log-probabilities of the start positions are always computed (init_lp = 1). */
+int mtg_ensemble_injected_host(const mtg_model_t *model, int N, int S, int E, int W,
+                               const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
+                               double *pos, double *lp, int nsteps, double a,
+                               const int32_t *split, const double *uz, const int32_t *rint, const double *uacc,
+                               double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags);
+
 /* ---- batched periodograms of an ensemble ---------------------------------
  * mtg_power_spectrum_host: |rfft(rate)|^2 of L regularly sampled lightcurves rates[L][n] -> out_power[L][n/2+1]
  *   (replaces the per-lightcurve numpy.fft.rfft loops of tests/simulator_test.py:24-35 and

@@ -119,6 +119,8 @@ SIGNATURES = {
     "mtg_ensemble_host": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
                                          _vp, _vp, _vp, ctypes.c_uint32]),
+    "mtg_ensemble_injected_host": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                  ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32]),
     "mtg_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "mtg_host_free": (ctypes.c_int, [_vp]),
     "mtg_test_math_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),

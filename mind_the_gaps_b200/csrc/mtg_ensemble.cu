@@ -103,17 +103,21 @@ k8_ensemble(const __grid_constant__ Plan pl, const EnsembleArgs a)
     for (int it = 0; it < a.nsteps; ++it) {
         const uint64_t step = a.step0 + (uint64_t)it;
         // ---- random split: rank of a random key (ties broken by index) = a uniformly random permutation ----
-        for (int idx = tid; idx < n_ens * W; idx += T) {
-            const uint32_t ee = (uint32_t)(e0 + idx / W) * 0x9E3779B9u;
-            key[idx] = philox4x32_10(make_uint4((uint32_t)(idx % W), 2u, (uint32_t)step, (uint32_t)(step >> 32) ^ ee), pkey).x;
-        }
+        if (!a.inj.split)
+            for (int idx = tid; idx < n_ens * W; idx += T) {
+                const uint32_t ee = (uint32_t)(e0 + idx / W) * 0x9E3779B9u;
+                key[idx] = philox4x32_10(make_uint4((uint32_t)(idx % W), 2u, (uint32_t)step, (uint32_t)(step >> 32) ^ ee), pkey).x;
+            }
         __syncthreads();
         for (int idx = tid; idx < n_ens * W; idx += T) {
             const int sb = idx / W, w = idx % W;
-            const uint32_t *kk = key + (size_t)sb * W;
-            const uint32_t kw = kk[w];
             int r = 0;
-            for (int k = 0; k < W; ++k) { const uint32_t v = kk[k]; r += (v < kw) || (v == kw && k < w); }
+            if (a.inj.split) r = injected_rank(a.inj.split + ((size_t)(e0 + sb) * a.nsteps + it) * W, w, n0);
+            else {
+                const uint32_t *kk = key + (size_t)sb * W;
+                const uint32_t kw = kk[w];
+                for (int k = 0; k < W; ++k) { const uint32_t v = kk[k]; r += (v < kw) || (v == kw && k < w); }
+            }
             perm[(size_t)sb * W + r] = w;
         }
         __syncthreads();
@@ -125,17 +129,23 @@ k8_ensemble(const __grid_constant__ Plan pl, const EnsembleArgs a)
             double q[MTG_MAX_PARAMS];
             if (lane_on && slot < s_cnt) {
                 w = mperm[s_off + slot];
-                const uint4 r0 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
-                const uint4 r1 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h + 4u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
-                const double uz = u01_from_bits(r0.x, r0.y);
-                const double g = (a.a - 1.0) * uz + 1.0;
-                const double zz = g * g / a.a;                                   // StretchMove: ((a-1) U + 1)^2 / a
-                const int j = c_off + (int)(((uint64_t)r0.z * (uint64_t)c_cnt) >> 32);      // randint(Nc)
+                double uz, uacc; int rj;
+                if (a.inj.split) {
+                    const size_t at = (((size_t)e * a.nsteps + it) * 2 + h) * n0 + slot;
+                    uz = a.inj.uz[at]; rj = a.inj.rint[at]; uacc = a.inj.uacc[at];
+                } else {
+                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
+                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h + 4u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
+                    uz = u01_from_bits(r0.x, r0.y);
+                    rj = (int)(((uint64_t)r0.z * (uint64_t)c_cnt) >> 32);        // randint(Nc)
+                    uacc = u01_from_bits(r1.x, r1.y);
+                }
+                const double zz = stretch_zz(a.a, uz);                           // StretchMove: ((a-1) U + 1)^2 / a
+                const int j = c_off + rj;
                 const double *pc = mpos + (size_t)mperm[j] * nd, *ps = mpos + (size_t)w * nd;
-                for (int k = 0; k < nd; ++k) q[k] = pc[k] - (pc[k] - ps[k]) * zz;
+                for (int k = 0; k < nd; ++k) q[k] = stretch_q(pc[k], ps[k], zz);
                 lq = k8_log_prob<JR, JC, DUAL>(pl, a, tb, q, ds_of(e));
-                const double lnpdiff = (double)(nd - 1) * log(zz) + lq - mlp[w];
-                accept = log(u01_from_bits(r1.x, r1.y)) < lnpdiff;               // NaN compares false
+                accept = log(uacc) < stretch_lnpdiff(nd, zz, lq, mlp[w]);        // NaN compares false
             }
             __syncthreads();          // every proposal of this half has read the positions it needs
             if (accept) {
@@ -202,11 +212,11 @@ static int launch_k8(const Plan &pl, const EnsembleArgs &a, cudaStream_t stream)
 }
 #define K8_CASE(R, C) if (pl.jr == R && pl.jc == C) return launch_k8<R, C>(pl, a, stream);
 
-extern "C" int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, int W,
-                                const double *t, const double *y, const double *diag, const double *ds_mean,
-                                double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
-                                double *chain, double *chain_lp, int32_t *n_accept, double *best_lp, double *best_pos,
-                                uint32_t flags, void *stream_)
+static int ensemble_run_dev(const mtg_model_t *model, int N, int S, int E, int W,
+                            const double *t, const double *y, const double *diag, const double *ds_mean,
+                            double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
+                            double *chain, double *chain_lp, int32_t *n_accept, double *best_lp, double *best_pos,
+                            uint32_t flags, const EnsembleInject *inj, void *stream_)
 {
     if (!model || N < 1 || S < 1 || E < 0 || W < 2 || nsteps < 0 || !t || !y || !diag || !pos || !lp || !(a_scale > 1.0)) {
         mtg_set_error("mtg_ensemble_dev: bad argument"); return MTG_EINVAL;
@@ -220,7 +230,8 @@ extern "C" int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, i
     if (rc) return rc;
     if (pl.n_free < 1) { mtg_set_error("mtg_ensemble_dev: the model has no free parameters"); return MTG_EINVAL; }
     if (W < 2 * pl.n_free) { mtg_set_error("the number of walkers must be at least twice the dimension (got %d for ndim=%d)", W, pl.n_free); return MTG_EINVAL; }
-    EnsembleArgs a{N, S, E, W, nsteps, t, y, diag, ds_mean, pos, lp, chain, chain_lp, n_accept, best_lp, best_pos, a_scale, seed, step0, flags, init_lp, 1};
+    EnsembleArgs a{N, S, E, W, nsteps, t, y, diag, ds_mean, pos, lp, chain, chain_lp, n_accept, best_lp, best_pos, a_scale, seed, step0, flags, init_lp, 1,
+                   inj ? *inj : EnsembleInject{nullptr, nullptr, nullptr, nullptr}};
     cudaStream_t stream = (cudaStream_t)stream_;
     // Few ensembles (derive_posteriors on ONE lightcurve): K8 would run each half ensemble as a 1000-step chain on one
     // warp.  K10 gives every proposal a whole CTA (parallel-in-time scan, mtg_scan.cu) and separates the half steps by a
@@ -237,17 +248,44 @@ extern "C" int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, i
     return MTG_EUNSUP;
 }
 
+extern "C" int mtg_ensemble_dev(const mtg_model_t *model, int N, int S, int E, int W,
+                                const double *t, const double *y, const double *diag, const double *ds_mean,
+                                double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
+                                double *chain, double *chain_lp, int32_t *n_accept, double *best_lp, double *best_pos,
+                                uint32_t flags, void *stream_)
+{
+    return ensemble_run_dev(model, N, S, E, W, t, y, diag, ds_mean, pos, lp, init_lp, nsteps, a_scale, seed, step0, chain, chain_lp,
+                            n_accept, best_lp, best_pos, flags, nullptr, stream_);
+}
+
 // Host-buffer entry point: y, diag are [S][N] ROW-major on the host (one lightcurve per row), transposed here.
-extern "C" int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
-                                 const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
-                                 double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
-                                 double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags)
+// inj_*: host arrays of injected draws (all or none), see EnsembleInject.
+static int ensemble_host_impl(const mtg_model_t *model, int N, int S, int E, int W,
+                              const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
+                              double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
+                              double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags,
+                              const int32_t *inj_split, const double *inj_uz, const int32_t *inj_rint, const double *inj_uacc)
 {
     if (!model || N < 1 || S < 1 || E < 1 || !t || !y_rows || !diag_rows || !pos || !lp) { mtg_set_error("mtg_ensemble_host: bad argument"); return MTG_EINVAL; }
     const int nd = model->n_free;
     cudaStream_t st = nullptr;
     MTG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     int rc = mtg_pool_setup();
+    // injected draws (test hook): one device block [split | rint | uz | uacc]
+    EnsembleInject inj{nullptr, nullptr, nullptr, nullptr};
+    unsigned char *d_inj = nullptr;
+    if (inj_split) {
+        const size_t H = (size_t)(W + 1) / 2, n_sp = (size_t)E * nsteps * W, n_h = (size_t)E * nsteps * 2 * H;
+        const size_t off_ri = n_sp * 4, off_uz = (off_ri + n_h * 4 + 7) / 8 * 8, off_ua = off_uz + n_h * 8;
+        if (!rc) rc = mtg_cuda_check(cudaMallocAsync((void **)&d_inj, off_ua + n_h * 8 + 8, st), "cudaMallocAsync");
+        if (rc) { cudaStreamDestroy(st); return rc; }
+        cudaMemcpyAsync(d_inj, inj_split, n_sp * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_inj + off_ri, inj_rint, n_h * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_inj + off_uz, inj_uz, n_h * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_inj + off_ua, inj_uacc, n_h * 8, cudaMemcpyHostToDevice, st);
+        inj.split = (const int32_t *)d_inj; inj.rint = (const int32_t *)(d_inj + off_ri);
+        inj.uz = (const double *)(d_inj + off_uz); inj.uacc = (const double *)(d_inj + off_ua);
+    }
     double *d = nullptr; int32_t *d_acc = nullptr;
     const size_t n_t = N, n_y = (size_t)N * S, n_pos = (size_t)E * W * nd, n_lp = (size_t)E * W, n_mean = ds_mean ? S : 0;
     const size_t n_chain = chain ? (size_t)E * nsteps * W * nd : 0, n_clp = chain_lp ? (size_t)E * nsteps * W : 0;
@@ -274,8 +312,8 @@ extern "C" int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, 
     if (n_mean) cudaMemcpyAsync(d_mean, ds_mean, n_mean * sizeof(double), cudaMemcpyHostToDevice, st);
     if (n_accept) cudaMemcpyAsync(d_acc, n_accept, n_lp * sizeof(int32_t), cudaMemcpyHostToDevice, st);
     else cudaMemsetAsync(d_acc, 0, n_lp * sizeof(int32_t), st);
-    rc = mtg_ensemble_dev(model, N, S, E, W, d_t, d_y, d_dg, n_mean ? d_mean : nullptr, d_pos, d_lp, init_lp, nsteps, a_scale, seed, step0,
-                          chain ? d_chain : nullptr, chain_lp ? d_clp : nullptr, d_acc, nullptr, nullptr, flags, st);
+    rc = ensemble_run_dev(model, N, S, E, W, d_t, d_y, d_dg, n_mean ? d_mean : nullptr, d_pos, d_lp, init_lp, nsteps, a_scale, seed, step0,
+                          chain ? d_chain : nullptr, chain_lp ? d_clp : nullptr, d_acc, nullptr, nullptr, flags, inj_split ? &inj : nullptr, st);
     if (!rc) {
         cudaMemcpyAsync(pos, d_pos, n_pos * sizeof(double), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(lp, d_lp, n_lp * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -285,7 +323,45 @@ extern "C" int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, 
         rc = mtg_cuda_check(cudaStreamSynchronize(st), "mtg_ensemble_host sync");
     }
     cudaFreeAsync(d, st); cudaFreeAsync(d_acc, st);
+    if (d_inj) cudaFreeAsync(d_inj, st);
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
     return rc;
+}
+
+extern "C" int mtg_ensemble_host(const mtg_model_t *model, int N, int S, int E, int W,
+                                 const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
+                                 double *pos, double *lp, int init_lp, int nsteps, double a_scale, uint64_t seed, uint64_t step0,
+                                 double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags)
+{
+    return ensemble_host_impl(model, N, S, E, W, t, y_rows, diag_rows, ds_mean, pos, lp, init_lp, nsteps, a_scale, seed, step0,
+                              chain, chain_lp, n_accept, flags, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mtg_ensemble_injected_host(const mtg_model_t *model, int N, int S, int E, int W,
+                                          const double *t, const double *y_rows, const double *diag_rows, const double *ds_mean,
+                                          double *pos, double *lp, int nsteps, double a_scale,
+                                          const int32_t *split, const double *uz, const int32_t *rint, const double *uacc,
+                                          double *chain, double *chain_lp, int32_t *n_accept, uint32_t flags)
+{
+    if (!split || !uz || !rint || !uacc) { mtg_set_error("mtg_ensemble_injected_host: the four draw arrays are required"); return MTG_EINVAL; }
+    const int H = (W + 1) / 2;
+    for (size_t es = 0; es < (size_t)E * nsteps; ++es) {           // validate: ceil(W/2) zeros per split, partners inside the complement
+        int zeros = 0;
+        for (int w = 0; w < W; ++w) {
+            const int v = split[es * W + w];
+            if (v != 0 && v != 1) { mtg_set_error("mtg_ensemble_injected_host: split entries must be 0 or 1"); return MTG_EINVAL; }
+            zeros += (v == 0);
+        }
+        if (zeros != H) { mtg_set_error("mtg_ensemble_injected_host: every split needs ceil(W/2) zeros"); return MTG_EINVAL; }
+        for (int h = 0; h < 2; ++h) {
+            const int ns = h == 0 ? H : W - H, nc = W - ns;
+            for (int i = 0; i < ns; ++i) {
+                const int r = rint[(es * 2 + h) * H + i];
+                if (r < 0 || r >= nc) { mtg_set_error("mtg_ensemble_injected_host: rint out of range"); return MTG_EINVAL; }
+            }
+        }
+    }
+    return ensemble_host_impl(model, N, S, E, W, t, y_rows, diag_rows, ds_mean, pos, lp, 1, nsteps, a_scale, 0, 0,
+                              chain, chain_lp, n_accept, flags, split, uz, rint, uacc);
 }

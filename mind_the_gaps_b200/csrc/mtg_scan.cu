@@ -748,13 +748,17 @@ k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigne
     for (int it = 0; it < a.nsteps; ++it) {
         const uint64_t step = a.step0 + (uint64_t)it;
         // random split of the ensemble: rank of a random key = a uniformly random permutation (every CTA redoes it)
-        for (int idx = tid; idx < W; idx += T)
-            key[idx] = philox4x32_10(make_uint4((uint32_t)idx, 2u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey).x;
+        if (!a.inj.split)
+            for (int idx = tid; idx < W; idx += T)
+                key[idx] = philox4x32_10(make_uint4((uint32_t)idx, 2u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey).x;
         __syncthreads();
         for (int w = tid; w < W; w += T) {
-            const uint32_t kw = key[w];
             int r = 0;
-            for (int k = 0; k < W; ++k) { const uint32_t v = key[k]; r += (v < kw) || (v == kw && k < w); }
+            if (a.inj.split) r = injected_rank(a.inj.split + ((size_t)e * a.nsteps + it) * W, w, n0);
+            else {
+                const uint32_t kw = key[w];
+                for (int k = 0; k < W; ++k) { const uint32_t v = key[k]; r += (v < kw) || (v == kw && k < w); }
+            }
             perm[r] = w;
         }
         __syncthreads();
@@ -763,23 +767,29 @@ k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigne
             const int c_off = h == 0 ? n0 : 0, c_cnt = W - s_cnt;
             if (slot < s_cnt) {
                 const int w = perm[s_off + slot];
-                const uint4 r0 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
-                const uint4 r1 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h + 4u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
-                const double uz = u01_from_bits(r0.x, r0.y);
-                const double g = (a.a - 1.0) * uz + 1.0;
-                const double zz = g * g / a.a;                                   // StretchMove: ((a-1) U + 1)^2 / a
-                const int j = c_off + (int)(((uint64_t)r0.z * (uint64_t)c_cnt) >> 32);      // randint(Nc)
+                double uz, uacc; int rj;
+                if (a.inj.split) {
+                    const size_t at = (((size_t)e * a.nsteps + it) * 2 + h) * n0 + slot;
+                    uz = a.inj.uz[at]; rj = a.inj.rint[at]; uacc = a.inj.uacc[at];
+                } else {
+                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
+                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)h + 4u, (uint32_t)step, (uint32_t)(step >> 32) ^ ekey), pkey);
+                    uz = u01_from_bits(r0.x, r0.y);
+                    rj = (int)(((uint64_t)r0.z * (uint64_t)c_cnt) >> 32);        // randint(Nc)
+                    uacc = u01_from_bits(r1.x, r1.y);
+                }
+                const double zz = stretch_zz(a.a, uz);                           // StretchMove: ((a-1) U + 1)^2 / a
+                const int j = c_off + rj;
                 if (tid < nd) {
                     const double pc = __ldcg(pos_e + (size_t)perm[j] * nd + tid), p0 = __ldcg(pos_e + (size_t)w * nd + tid);
                     ps[tid] = p0;
-                    q[tid] = pc - (pc - p0) * zz;
+                    q[tid] = stretch_q(pc, p0, zz);
                 }
                 __syncthreads();
                 const double lq = log_prob(q);
                 if (tid == 0) {
                     const double lpw = __ldcg(lp_e + w);
-                    const double lnpdiff = (double)(nd - 1) * log(zz) + lq - lpw;
-                    const bool accept = log(u01_from_bits(r1.x, r1.y)) < lnpdiff;           // NaN compares false
+                    const bool accept = log(uacc) < stretch_lnpdiff(nd, zz, lq, lpw);       // NaN compares false
                     if (accept) {
                         for (int k = 0; k < nd; ++k) __stcg(pos_e + (size_t)w * nd + k, q[k]);
                         __stcg(lp_e + w, lq);

@@ -130,7 +130,18 @@ def loglike_params(spec, params, t, y, dy, mean=None, fit_mean=False, dense=Fals
     y = np.asarray(y, dtype=float)
     diag = (np.asarray(dy, dtype=float) + 1e-12) ** 2
     nk = _terms.n_params(spec)
-    if fit_mean:
+    if fit_mean in ("linear", "gaussian"):
+        # the fitted mean models of GPModelling._build_mean_model (gpmodelling.py:98-122) with the expressions of
+        # models/mean_models.py:9-10 (GaussianModel: amplitude / (2 pi sigma) exp(-(t - mean)^2 / (2 sigma^2)) + constant)
+        # and :26-27 (LinearModel: slope t + intercept); parameters follow the kernel's in the vector
+        tt = np.asarray(t, dtype=float)[None, :]
+        if fit_mean == "linear":
+            mu = p[:, nk, None] * tt + p[:, nk + 1, None]
+        else:
+            m0, sg, am, c0 = (p[:, nk + i, None] for i in range(4))
+            mu = am / (2 * np.pi * sg) * np.exp(-(tt - m0) ** 2 / (2 * sg ** 2)) + c0
+        resid = y[None, :] - mu
+    elif fit_mean:
         mu = p[:, nk]
         resid = y[None, :] - mu[:, None]
     else:
@@ -153,6 +164,8 @@ def grad_complex_step(spec, params, t, y, dy, mean=None, fit_mean=False, h=1e-30
     g = np.empty((B, ndim))
     for k in range(ndim):
         pc = p.astype(np.complex128)
+        # (the imaginary part travels separately from the real one, so h = 1e-30 works for parameters of any magnitude:
+        #  mean-model parameters span 1e-10 .. 1e9 here)
         pc[:, k] += 1j * h
         ll = loglike_params(spec, pc, t, y, dy, mean=mean, fit_mean=fit_mean)
         g[:, k] = np.imag(ll) / h

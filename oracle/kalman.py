@@ -117,3 +117,110 @@ def grad_complex_step_scan(spec, params, t, resid, diag, h=1e-30, threads=64):
         jit = co[6] if len(co) > 6 else 0.0
         g[k] = np.imag(loglike_scan(t, resid, diag + jit, statespace(ar, cr, ac, bc, cc, dc), threads=threads)) / h
     return g
+
+
+# ---- reverse mode through the filter, chunk by chunk: the NumPy statement of kernel K11 (csrc/mtg_scan_grad.cu) ------------
+def _blocks(ar, cr, ac, bc, cc, dc):
+    """(kind, first row, coefficient index) per state-space block, in statespace()'s order"""
+    out = []; i = 0
+    for j in range(len(ar)):
+        if np.real(ar[j]) != 0.0:
+            out.append(("r", i, j)); i += 1
+    for j in range(len(ac)):
+        out.append(("c", i, j)); i += 2
+    return out, i
+
+
+def _step_adjoint(lam, Lam, m_prev, P_prev, F, Pinf, h, y, R, first):
+    """Adjoint of one filter step.  In: adjoints (lam, Lam) of the FILTERED mean / covariance after the step
+    (d loglike = lam . dm + sum_ij Lam_ij dP_ij, Lam symmetric) and the step's inputs.  Out: adjoints of the previous
+    filtered state, and of F, P_inf, R and the residual y."""
+    mm = F @ m_prev; X = P_prev - Pinf; Pm = F @ X @ F.T + Pinf
+    g = Pm @ h; s = h @ g + R; v = y - h @ mm
+    lg = lam @ g
+    vb = (lg - v) / s
+    sb = (-lg * v + g @ Lam @ g) / (s * s) + 0.5 * v * v / (s * s) - 0.5 / s
+    gb = lam * (v / s) - 2.0 * (Lam @ g) / s + sb * h
+    mb = lam - vb * h
+    Pb = Lam + 0.5 * (np.outer(gb, h) + np.outer(h, gb))
+    lam_prev = F.T @ mb
+    Lam_prev = F.T @ Pb @ F
+    Pinf_b = Pb - Lam_prev
+    F_b = np.zeros_like(F) if first else 2.0 * Pb @ F @ X + np.outer(mb, m_prev)
+    return lam_prev, Lam_prev, F_b, Pinf_b, sb, vb
+
+
+def grad_chunked_adjoint(t, resid, diag, ar, cr, ac, bc, cc, dc, jitter=0.0, threads=8):
+    """log-likelihood and its gradient with respect to the celerite coefficients, the jitter and the residuals, with the
+    structure of kernel K11: (1) forward filter (the kernel gets every chunk's start state from the scan; here it is simply
+    run in order), recording per chunk the closed-loop transition ``Phi = prod (I - K h^T) F`` and the backward information
+    ``q = sum w v / s``, ``Omega = sum w w^T / s`` (``w = Psi^T F^T h``); (2) a SUFFIX scan over the chunks with the
+    associative operator ``(a then b) -> (Phi_b Phi_a, Phi_a^T q_b + q_a, Phi_a^T Omega_b Phi_a + Omega_a)`` gives the
+    adjoint of every chunk's end state in closed form, ``lam = q_suf``, ``Lam = (q_suf q_suf^T - Omega_suf) / 2``; (3) every
+    chunk runs the step adjoints over its own observations independently.  Returns ``(ll, dict of gradients)``."""
+    ar, cr, ac, bc, cc, dc = [np.atleast_1d(np.asarray(x, dtype=float)) for x in (ar, cr, ac, bc, cc, dc)]
+    J, Pinf, h, transition = statespace(ar, cr, ac, bc, cc, dc)
+    blocks, _ = _blocks(ar, cr, ac, bc, cc, dc)
+    N = len(t)
+    ch = -(-N // threads)
+    bounds = [(min(k * ch, N), min(k * ch + ch, N)) for k in range(threads)]
+    # (1) forward
+    m, P, ll = np.zeros(J), Pinf.copy(), 0.0
+    tape = [None] * N
+    elems = []
+    for (n0, n1) in bounds:
+        Psi = np.eye(J); q = np.zeros(J); Om = np.zeros((J, J))
+        for n in range(n0, n1):
+            F = transition(t[n] - t[n - 1]) if n else np.eye(J)
+            R = diag[n] + jitter
+            tape[n] = (m, P, F, R)
+            mm = F @ m; Pm = F @ (P - Pinf) @ F.T + Pinf
+            g = Pm @ h; s = h @ g + R; v = resid[n] - h @ mm
+            w = (F @ Psi).T @ h
+            q = q + w * (v / s); Om = Om + np.outer(w, w) / s
+            Psi = (np.eye(J) - np.outer(g, h) / s) @ F @ Psi
+            m = mm + g * (v / s); P = Pm - np.outer(g, g) / s
+            ll += -0.5 * (v * v / s + np.log(s) + np.log(2 * np.pi))
+        elems.append((Psi, q, Om))
+    # (2) exclusive suffix composites
+    suf = [None] * threads
+    acc = (np.eye(J), np.zeros(J), np.zeros((J, J)))
+    for k in range(threads - 1, -1, -1):
+        suf[k] = acc
+        Pa, qa, Oa = elems[k]; Pb, qb, Ob = acc
+        acc = (Pb @ Pa, Pa.T @ qb + qa, Pa.T @ Ob @ Pa + Oa)
+    # (3) per-chunk adjoint sweeps
+    g_ar = np.zeros(len(ar)); g_cr = np.zeros(len(cr)); g_ac = np.zeros(len(ac)); g_bc = np.zeros(len(ac))
+    g_cc = np.zeros(len(ac)); g_dc = np.zeros(len(ac)); g_jit = 0.0; g_res = np.zeros(N)
+    for k, (n0, n1) in enumerate(bounds):
+        _, qs, Os = suf[k]
+        lam = qs.copy(); Lam = 0.5 * (np.outer(qs, qs) - Os)
+        for n in range(n1 - 1, n0 - 1, -1):
+            m_prev, P_prev, F, R = tape[n]
+            lam, Lam, F_b, Pinf_b, sb, vb = _step_adjoint(lam, Lam, m_prev, P_prev, F, Pinf, h, resid[n], R, n == 0)
+            g_jit += sb; g_res[n] = vb
+            dt = t[n] - t[n - 1] if n else 0.0
+            for kind, i, j in blocks:
+                if kind == "r":
+                    g_ar[j] += Pinf_b[i, i]; g_cr[j] += -dt * F[i, i] * F_b[i, i]
+                else:
+                    a, b, c, d = ac[j], bc[j], cc[j], dc[j]
+                    Fb = F_b[i:i + 2, i:i + 2]; Fk = F[i:i + 2, i:i + 2]; Pb = Pinf_b[i:i + 2, i:i + 2]
+                    g_cc[j] += -dt * np.sum(Fb * Fk)
+                    # dF/dd = dt e [[-sn, cs], [-cs, -sn]] = dt [[F01, F00], [-F00, F01]] with F00 = e cs, F01 = e sn
+                    g_dc[j] += dt * (-Fk[0, 1] * Fb[0, 0] + Fk[0, 0] * Fb[0, 1] - Fk[0, 0] * Fb[1, 0] - Fk[0, 1] * Fb[1, 1])
+                    g_ac[j] += Pb[0, 0] + Pb[1, 1]
+                    g_bc[j] += Pb[0, 1] + Pb[1, 0]
+                    if b != 0.0:
+                        g_bc[j] += Pb[1, 1] * 2.0 * c / d; g_cc[j] += Pb[1, 1] * 2.0 * b / d; g_dc[j] += -Pb[1, 1] * 2.0 * c * b / (d * d)
+        if k == 0:                                   # the prior covariance IS P_inf
+            for kind, i, j in blocks:
+                if kind == "r":
+                    g_ar[j] += Lam[i, i]
+                else:
+                    a, b, c, d = ac[j], bc[j], cc[j], dc[j]
+                    Pb = Lam[i:i + 2, i:i + 2]
+                    g_ac[j] += Pb[0, 0] + Pb[1, 1]; g_bc[j] += Pb[0, 1] + Pb[1, 0]
+                    if b != 0.0:
+                        g_bc[j] += Pb[1, 1] * 2.0 * c / d; g_cc[j] += Pb[1, 1] * 2.0 * b / d; g_dc[j] += -Pb[1, 1] * 2.0 * c * b / (d * d)
+    return ll, {"ar": g_ar, "cr": g_cr, "ac": g_ac, "bc": g_bc, "cc": g_cc, "dc": g_dc, "jitter": g_jit, "resid": g_res}

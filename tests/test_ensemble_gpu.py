@@ -128,3 +128,52 @@ def test_gpmodelling_derive_posteriors_uses_the_device_sampler():
     # the maximum of the chain cannot be far below the MLE and never above it by more than rounding
     fit = gpm.fit(gpm.median_parameters)
     assert gpm.max_loglikelihood <= -fit.fun + 1e-6 and gpm.max_loglikelihood > -fit.fun - 5.0
+
+
+@pytest.mark.parametrize("kernel_flag", ["k8", "scan"])
+@pytest.mark.parametrize("W", [12, 11])
+def test_chain_on_injected_draws_equals_the_emcee_restatement(kernel_flag, W):
+    """Sampler parity proper: K8 and K10 fed the draws emcee 3.1.4 would take from its RandomState (split, stretch
+    variates, partner indices, accept uniforms -- oracle.sampler.draws_like_emcee) walk the SAME chain as the NumPy
+    restatement of RedBlueMove / StretchMove driving the oracle's log-probability: positions bit for bit, stored
+    log-probabilities to rounding.  Two ensembles on two lightcurves, even and odd ensemble sizes."""
+    import ctypes
+    from mind_the_gaps_b200 import _native
+    from oracle import sampler as osamp
+    N, E, nsteps = 120, 2, 60
+    t, y0, dy0, _ = fake_lightcurve(N, 4)
+    _, y1, dy1, _ = fake_lightcurve(N, 9)
+    Y = np.ascontiguousarray(np.stack([y0, y1])); DY = np.stack([dy0, dy1])
+    kernel = DampedRandomWalk(-6.0, -13.5, bounds=B_DRW) + Lorentzian(-7.0, 2.0, -12.5, bounds=dict(log_S0=(-14, 2), log_Q=(0.0, 6.0), log_omega0=(-16, -9)))
+    gp = GP(kernel, mean=0.0)
+    model = gp.device_model()
+    nd = model.n_free
+    bounds = gp.get_parameter_bounds()
+    spec = [("drw",), ("lorentzian",)]
+    means = np.ascontiguousarray(Y.mean(axis=1))
+    rs = np.random.RandomState(123)
+    p0 = gp.get_parameter_vector()[None, None, :] + rs.normal(0, 0.05, (E, W, nd))
+    H = (W + 1) // 2
+    draws = [osamp.draws_like_emcee(rs, W, nsteps) for _ in range(E)]
+    split = np.ascontiguousarray(np.stack([d[0] for d in draws]), dtype=np.int32)
+    uz = np.ascontiguousarray(np.stack([d[1] for d in draws])); rint = np.ascontiguousarray(np.stack([d[2] for d in draws]), dtype=np.int32)
+    uacc = np.ascontiguousarray(np.stack([d[3] for d in draws]))
+    assert uz.shape == (E, nsteps, 2, H)
+    pos = np.ascontiguousarray(p0.copy()); lp = np.empty((E, W))
+    chain = np.empty((E, nsteps, W, nd)); chain_lp = np.empty((E, nsteps, W)); nacc = np.zeros((E, W), dtype=np.int32)
+    diag = np.ascontiguousarray((DY + 1e-12) ** 2)
+    flag = {"k8": _native.FLAG_NO_SCAN, "scan": _native.FLAG_SCAN}[kernel_flag] | _native.FLAG_DS_MEAN
+    _native.check(_native.lib().mtg_ensemble_injected_host(
+        ctypes.byref(model), N, E, E, W, _native.ptr(np.ascontiguousarray(t)), _native.ptr(Y), _native.ptr(diag), _native.ptr(means),
+        _native.ptr(pos), _native.ptr(lp), nsteps, 2.0, _native.ptr(split), _native.ptr(uz), _native.ptr(rint), _native.ptr(uacc),
+        _native.ptr(chain), _native.ptr(chain_lp), _native.ptr(nacc), flag))
+    for e in range(E):
+        def logp(x, e=e):
+            out = ogp.log_prior(x, bounds) + np.real(ogp.loglike_params(spec, x, t, Y[e], DY[e]))
+            return np.where(np.isfinite(out), out, -np.inf)
+        ref_chain, ref_lp, ref_acc = osamp.stretch_move_run(logp, p0[e], nsteps, *draws[e])
+        np.testing.assert_array_equal(chain[e], ref_chain)
+        np.testing.assert_allclose(chain_lp[e], ref_lp, rtol=1e-11)
+        np.testing.assert_array_equal(nacc[e], ref_acc)
+        np.testing.assert_array_equal(pos[e], ref_chain[-1])
+        assert 0.1 < ref_acc.mean() / nsteps < 0.9

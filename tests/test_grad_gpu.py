@@ -118,3 +118,58 @@ def test_chunked_tape_gives_identical_results(monkeypatch):
     monkeypatch.setenv("MTG_TAPE_MB", "8")
     ll1, g1 = gp.grad_log_likelihood_batch(y, p)
     assert np.array_equal(ll0, ll1) and np.array_equal(g0, g1)
+
+
+@pytest.mark.parametrize("segment", [None, "3"])
+def test_gradient_at_c2_size(monkeypatch, segment):
+    """config C2's own shape: N = 1000, DRW + Lorentzian, against complex-step; the reverse sweep's last segment is a
+    partial one both with the default segment length (1000 % 6 = 4) and with a forced 3 (1000 % 3 = 1)."""
+    if segment:
+        monkeypatch.setenv("MTG_K2_SEGMENT", segment)
+    t, y, dy, _ = fake_lightcurve(1000, 2)
+    kernel, spec = build("drw+lor")
+    gp = GP(kernel, mean=ConstantModel(float(np.mean(y))), fit_mean=False)
+    gp.compute(t, dy + 1e-12)
+    p = c2_truth()[None, :] + np.random.default_rng(12).normal(0, 0.1, (24, 5))
+    ll, g, status = gp.grad_log_likelihood_batch(y, p, return_status=True)
+    assert np.all(status == 0)
+    np.testing.assert_allclose(ll, ogp.loglike_params(spec, p, t, y, dy), rtol=1e-10)
+    assert_grad_close(g, ogp.grad_complex_step(spec, p, t, y, dy))
+
+
+@pytest.mark.parametrize("mean_model", ["gaussian", "linear", "constant"])
+def test_gpmodelling_fitted_mean_models_against_oracle(mean_model):
+    """GPModelling(lc, kernel, mean_model=...) (gpmodelling.py:62-124): log-probability and gradient of the model
+    GPModelling builds -- kernel parameters followed by the mean model's -- against the oracle with the same mean."""
+    from mind_the_gaps_b200.gpmodelling import GPModelling
+    from mind_the_gaps_b200.lightcurves import GappyLightcurve
+    t, y, dy, exposures = fake_lightcurve(300, 41)
+    bump = 0.2 * np.exp(-0.5 * ((t - t[150]) / (0.15 * (t[-1] - t[0]))) ** 2)
+    lc = GappyLightcurve(t, y + bump, dy, exposures)
+    kernel = DampedRandomWalk(np.log(0.002), np.log(2 * np.pi / (20 * 86400.0)), bounds=[(-15, 5), (-20, -5)])
+    gpm = GPModelling(lc, kernel, mean_model=mean_model)
+    p0 = gpm.gp.get_parameter_vector()
+    nm = {"gaussian": 4, "linear": 2, "constant": 1}[mean_model]
+    assert len(p0) == 2 + nm
+    rng = np.random.default_rng(3)
+    P = np.tile(p0, (12, 1))
+    P[:, :2] += rng.normal(0, 0.1, (12, 2))
+    if mean_model == "gaussian":
+        P[:, 2] += rng.normal(0, 0.02, 12) * (t[-1] - t[0]); P[:, 3] *= rng.uniform(0.3, 0.9, 12)
+        P[:, 4] *= rng.uniform(1.0, 2.0, 12); P[:, 5] += rng.normal(0, 0.01, 12)
+    elif mean_model == "linear":
+        P[:, 2] = rng.normal(0, 1e-9, 12); P[:, 3] = np.mean(lc.y) + rng.normal(0, 0.02, 12)
+    else:
+        P[:, 2] += rng.normal(0, 0.01, 12)
+    fit_mean = True if mean_model == "constant" else mean_model
+    ref = ogp.loglike_params([("drw",)], P, t, lc.y, dy, fit_mean=fit_mean)
+    got = gpm._log_probability(P)
+    inside = np.isfinite(got)
+    assert inside.sum() >= 6
+    np.testing.assert_allclose(got[inside], ref[inside], rtol=1e-10)
+    np.testing.assert_allclose([gpm._log_probability(row) for row in P[inside][:3]], ref[inside][:3], rtol=1e-10)
+    ll, g = gpm.gp.grad_log_likelihood_batch(lc.y, P[inside])
+    gref = ogp.grad_complex_step([("drw",)], P[inside], t, lc.y, dy, fit_mean=fit_mean)
+    # parameters of very different magnitude (times ~1e8 s, amplitudes ~1e7): compare each component on its own scale
+    err = np.abs(g - gref) / np.max(np.abs(gref), axis=0, keepdims=True)
+    assert np.max(err) < 1e-8, "scaled gradient error per parameter: %s" % np.max(err, axis=0)

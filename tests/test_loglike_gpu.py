@@ -236,3 +236,33 @@ def test_host_call_chunk_pipeline_matches_unpipelined_slices(S, group):
     idx = rng.choice(B, 64, replace=False)
     ref = np.array([ogp.loglike_params(spec, p[i:i + 1], t, Y[i // group if S > 1 else 0], DY[i // group if S > 1 else 0])[0] for i in idx])
     np.testing.assert_allclose(ll[idx], ref, rtol=RTOL)
+
+
+def test_c5_real_shape_parity_at_size():
+    """config C5 exactly as bench.py runs it: N = 1e5 points, 3 x SHOTerm + RealTerm (celerite J = 7, ndim = 11),
+    parameter sets = truth + N(0, 0.1).  K1 against (i) the NumPy recursion of the oracle on 4 parameter sets at full
+    length, (ii) the C restatement of celerite's two-pass solver on 32, (iii) the dense Cholesky on an N = 3000 prefix
+    (which pins the recursion itself at this width), and the status words."""
+    import bench
+    from oracle import cref
+    t, y, dy = bench.c5_workload(100000)
+    kernel = bench.c5_kernel()
+    spec = [("sho",), ("sho",), ("sho",), ("real",)]
+    gp = GP(kernel, mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    p0 = gp.get_parameter_vector()
+    assert len(p0) == 11
+    p = p0[None, :] + np.random.default_rng(7).normal(0, 0.1, (32, 11))
+    ll, status = gp.log_likelihood_batch(y, p, return_status=True, apply_prior=True)
+    assert np.all(status == 0) and np.all(np.isfinite(ll))
+    ref_c = cref.loglike_params(spec, p, t, y, dy)
+    np.testing.assert_allclose(ll, ref_c, rtol=RTOL)
+    ref_np = ogp.loglike_params(spec, p[:4], t, y, dy)
+    np.testing.assert_allclose(ll[:4], ref_np, rtol=RTOL)
+    # prefix against the dense Cholesky (the mean stays the full series' mean, as in the device call)
+    n = 3000
+    gp_s = GP(bench.c5_kernel(), mean=float(np.mean(y)))
+    gp_s.compute(t[:n], dy[:n] + 1e-12)
+    ll_s = gp_s.log_likelihood_batch(y[:n], p[:6])
+    ref_d = ogp.loglike_params(spec, p[:6], t[:n], y[:n], dy[:n], mean=float(np.mean(y)), dense=True)
+    np.testing.assert_allclose(ll_s, ref_d, rtol=1e-9)

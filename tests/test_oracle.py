@@ -151,3 +151,39 @@ def test_forward_mode_derivatives_survive_the_scan():
     g = kalman.grad_complex_step_scan(spec, p, t, y - np.mean(y), (dy + 1e-12) ** 2)
     ref = gp.grad_complex_step(spec, p[None, :], t, y, dy)[0]
     np.testing.assert_allclose(g, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+
+
+# ---- oracle.sampler: emcee 3.1.4's stretch move restated (gpmodelling.py:247-264) -----------------------------------------
+def test_oracle_sampler_draw_order_and_posterior():
+    """The restated stretch move (i) consumes the RandomState exactly as emcee does -- per iteration shuffle(inds), then per
+    half rand(Ns), randint(Nc, Ns) and one rand() per accept test -- and (ii) samples the right distribution: mean and
+    covariance of a correlated 2-d Gaussian."""
+    from oracle import sampler as osamp
+    W, nsteps = 10, 3
+    rs = np.random.RandomState(42)
+    split, uz, rint, uacc = osamp.draws_like_emcee(rs, W, nsteps)
+    rs2 = np.random.RandomState(42)
+    for it in range(nsteps):
+        inds = np.arange(W) % 2
+        rs2.shuffle(inds)
+        assert np.array_equal(split[it], inds) and inds.sum() == W // 2
+        for h in range(2):
+            ns = int(np.sum(inds == h))
+            np.testing.assert_array_equal(uz[it, h, :ns], rs2.rand(ns))
+            np.testing.assert_array_equal(rint[it, h, :ns], rs2.randint(W - ns, size=(ns,)))
+            np.testing.assert_array_equal(uacc[it, h, :ns], [rs2.rand() for _ in range(ns)])
+    cov = np.array([[1.0, 0.6], [0.6, 2.0]]); icov = np.linalg.inv(cov); mu = np.array([0.5, -1.0])
+    logp = lambda x: -0.5 * np.einsum("bi,ij,bj->b", x - mu, icov, x - mu)
+    W, nsteps = 32, 4000
+    rs = np.random.RandomState(7)
+    p0 = mu + rs.normal(0, 0.1, (W, 2))
+    chain, lp, nacc = osamp.stretch_move_run(logp, p0, nsteps, *osamp.draws_like_emcee(rs, W, nsteps))
+    flat = chain[500:].reshape(-1, 2)
+    np.testing.assert_allclose(lp[-1], logp(chain[-1]), rtol=1e-12)
+    assert np.all(np.abs(flat.mean(axis=0) - mu) < 0.08)
+    np.testing.assert_allclose(np.cov(flat.T), cov, atol=0.2)
+    assert 0.5 < nacc.mean() / nsteps < 0.85          # ~0.7 for a 2-d Gaussian with a = 2
+    # a proposal is c - (c - s) zz with zz = ((a - 1) u + 1)^2 / a: u = 0 contracts the walker towards its partner by 1/2
+    one = osamp.stretch_move_run(lambda x: np.zeros(len(x)), np.array([[0.0], [4.0]]), 1, np.array([[0, 1]]),
+                                 np.zeros((1, 2, 1)), np.zeros((1, 2, 1), dtype=int), np.zeros((1, 2, 1)))[0]
+    np.testing.assert_array_equal(one[0], [[2.0], [3.0]])

@@ -164,8 +164,8 @@ def test_lrt_flags_simulations_with_negative_expected_counts():
     """Gaussian-PDF simulation of a faint, highly variable source: some bins get rate * exposure < 0, where the reference's
     np.random.poisson raises ValueError('lam < 0') (noise_models.py:72).  The device pipeline flags those simulations."""
     lc, truth = make_lc(200, 4)
-    faint = GappyLightcurve(lc.times, lc.y * 0.2, lc.dy, lc.exposures)          # mean 0.1, sigma of the process 0.05..0.1
-    big = np.array([np.log(0.08 ** 2), truth[1]])
+    faint = GappyLightcurve(lc.times, lc.y * 0.2, lc.dy, lc.exposures)          # mean 0.1, sigma of the process 0.035: ~3 sigma from zero
+    big = np.array([np.log(0.035 ** 2), truth[1]])
     b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
     null_kernel = DampedRandomWalk(big[0], big[1], bounds=b_drw)
     alt_kernel = Lorentzian(big[0] - 2, np.log(20.0), np.log(2 * np.pi / (10 * DAY)),
