@@ -168,8 +168,13 @@ class GP(ModelSet):
         _native.check(rc)
         return (ll, status) if return_status else ll
 
-    def grad_log_likelihood_batch(self, y, params, apply_prior=False, return_status=False):
-        """``(loglike[B], grad[B, ndim])`` by the fused forward + reverse-mode kernel."""
+    _GRAD_KERNEL_FLAGS = {"auto": 0, "k2": _native.FLAG_NO_SCAN, "scan": _native.FLAG_SCAN}
+
+    def grad_log_likelihood_batch(self, y, params, apply_prior=False, return_status=False, kernel="auto"):
+        """``(loglike[B], grad[B, ndim])`` by reverse-mode differentiation on the device.
+
+        ``kernel``: ``"auto"`` (the library picks: the parallel-in-time scan gradient K11 -- one CTA per series -- for small
+        batches of narrow kernels, the one-thread-per-series kernel K2 otherwise), ``"k2"`` or ``"scan"`` to force one."""
         y = self._check_y(y)
         p = self._batch_params(params)
         B = p.shape[0]
@@ -178,7 +183,7 @@ class GP(ModelSet):
         ll = np.empty(B, dtype=np.float64)
         grad = np.empty((B, p.shape[1]), dtype=np.float64)
         status = np.empty(B, dtype=np.int32)
-        flags = _native.FLAG_APPLY_PRIOR if apply_prior else 0
+        flags = (_native.FLAG_APPLY_PRIOR if apply_prior else 0) | self._GRAD_KERNEL_FLAGS[kernel]
         rc = _native.lib().mtg_loglike_grad_host(ctypes.byref(model), len(self._t), 1, max(B, 1), B,
                                                  _native.ptr(self._t), _native.ptr(y), _native.ptr(self._diag), None,
                                                  _native.ptr(p), _native.ptr(ll), _native.ptr(grad),

@@ -198,6 +198,10 @@ __device__ __forceinline__ void fence_proxy_async()
 int    mtg_k1_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);
 int    mtg_k9_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);      // parallel-in-time scan (mtg_scan.cu)
 bool   mtg_k9_supports(const Plan &pl);
+int    mtg_k11_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);     // scan gradient (mtg_scan_grad.cu); honours a.index / a.count
+bool   mtg_k11_supports(const Plan &pl, int N);
+size_t mtg_k11_smem_bytes(const Plan &pl, int N);
+long long mtg_scan_grad_max_batch();
 size_t mtg_k2_tape_bytes_per_series(const Plan &pl, int N);
 int    mtg_k2_chunk(const Plan &pl, int N, int B);
 // a.B work items (series a.index[i] when a.index != NULL, limited to *a.count when a.count != NULL)

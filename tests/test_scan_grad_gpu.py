@@ -1,0 +1,109 @@
+"""GPU parity: K11 (parallel-in-time gradient: forward scan + suffix scan of the adjoint, one CTA per series) against
+complex-step differentiation of the oracle's celerite recursion and against K2.  north_star tolerance:
+1e-9 relative; asserted relative to the largest gradient component of each series."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from mind_the_gaps_b200 import _native
+from mind_the_gaps_b200.celerite import GP, terms
+from mind_the_gaps_b200.celerite.modeling import ConstantModel
+from mind_the_gaps_b200.models import DampedRandomWalk, GaussianModel, LinearModel
+from oracle import gp as ogp
+
+from helpers import c2_truth, fake_lightcurve
+from test_grad_gpu import assert_grad_close
+from test_loglike_gpu import build
+
+pytestmark = pytest.mark.gpu
+SCAN_KINDS = ["drw", "drw+lor", "complex+real", "sho_overdamped+jitter", "matern+real", "bpl+cos", "complex4"]
+
+
+@pytest.mark.parametrize("kind", SCAN_KINDS)
+@pytest.mark.parametrize("N", [1, 2, 255, 300, 1000])
+def test_scan_gradient_matches_complex_step(kind, N):
+    t, y, dy, _ = fake_lightcurve(max(N, 2), 31)
+    t, y, dy = t[:N], y[:N], dy[:N]
+    kernel, spec = build(kind)
+    gp = GP(kernel, mean=ConstantModel(float(np.mean(y))), fit_mean=False)
+    gp.compute(t, dy + 1e-12)
+    p0 = gp.get_parameter_vector()
+    B = 12 if N == 1000 else 40
+    p = p0[None, :] + np.random.default_rng(N + 1).normal(0, 0.05, (B, len(p0)))
+    if kind == "sho_overdamped+jitter":
+        p[:, 1] = np.log(0.2) + np.random.default_rng(1).normal(0, 0.05, B)
+    ll, g, status = gp.grad_log_likelihood_batch(y, p, return_status=True, kernel="scan")
+    assert np.all(status == 0)
+    np.testing.assert_allclose(ll, ogp.loglike_params(spec, p, t, y, dy), rtol=1e-10)
+    assert_grad_close(g, ogp.grad_complex_step(spec, p, t, y, dy))
+    ll2, g2 = gp.grad_log_likelihood_batch(y, p, kernel="k2")
+    np.testing.assert_allclose(ll, ll2, rtol=1e-12)
+    assert_grad_close(g, g2)
+
+
+def test_scan_gradient_sho_straddling_q_half():
+    t, y, dy, _ = fake_lightcurve(300, 5)
+    gp = GP(terms.SHOTerm(-6.0, 0.0, -12.0) + terms.RealTerm(-6.0, -13.0), mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    p = np.tile(gp.get_parameter_vector(), (32, 1))
+    p[:, 1] = np.log(np.r_[np.linspace(0.1, 0.45, 16), np.linspace(0.55, 3.0, 16)])
+    ll, g = gp.grad_log_likelihood_batch(y, p, kernel="scan")
+    spec = [("sho",), ("real",)]
+    ref = np.concatenate([ogp.grad_complex_step(spec, p[i:i + 1], t, y, dy) for i in range(32)])
+    assert_grad_close(g, ref)
+
+
+@pytest.mark.parametrize("meankind", ["constant", "linear", "gaussian"])
+def test_scan_gradient_with_fitted_mean(meankind):
+    t, y, dy, _ = fake_lightcurve(400, 32)
+    if meankind == "constant":
+        mean, fit = ConstantModel(float(np.mean(y))), True
+    elif meankind == "linear":
+        mean, fit = LinearModel(1e-10, 0.5), "linear"
+    else:
+        mean, fit = GaussianModel(float(t[200]), float(t[-1] - t[0]) / 4, 1e6, 0.5), "gaussian"
+    gp = GP(DampedRandomWalk(np.log(0.01), np.log(1e-6)), mean=mean, fit_mean=True)
+    gp.compute(t, dy + 1e-12)
+    p = np.tile(gp.get_parameter_vector(), (10, 1))
+    p[:, :2] += np.random.default_rng(2).normal(0, 0.05, (10, 2))
+    ll, g = gp.grad_log_likelihood_batch(y, p, kernel="scan")
+    gref = ogp.grad_complex_step([("drw",)], p, t, y, dy, fit_mean=fit)
+    err = np.abs(g - gref) / np.max(np.abs(gref), axis=0, keepdims=True)
+    assert np.max(err) < 1e-8, "scaled gradient error per parameter: %s" % np.max(err, axis=0)
+
+
+def test_scan_gradient_per_dataset_layout_and_longer_series():
+    N, S, group = 1537, 5, 3
+    t, _, _, _ = fake_lightcurve(N, 34)
+    rng = np.random.default_rng(5)
+    Y = 0.5 + 0.05 * rng.normal(size=(S, N)); DY = rng.uniform(0.01, 0.03, (S, N))
+    kernel, spec = build("drw+lor")
+    model = GP(kernel, mean=0.0).device_model()
+    B = S * group
+    p = c2_truth()[None, :] + rng.normal(0, 0.1, (B, 5))
+    ll = np.empty(B); g = np.empty((B, 5)); st = np.empty(B, dtype=np.int32)
+    diag = np.ascontiguousarray((DY + 1e-12) ** 2); means = np.ascontiguousarray(Y.mean(axis=1))
+    _native.check(_native.lib().mtg_loglike_grad_host(
+        ctypes.byref(model), N, S, group, B, _native.ptr(np.ascontiguousarray(t)), _native.ptr(Y), _native.ptr(diag),
+        _native.ptr(means), _native.ptr(p), _native.ptr(ll), _native.ptr(g), _native.ptr(st), _native.FLAG_DS_MEAN | _native.FLAG_SCAN))
+    assert np.all(st == 0)
+    ref = np.concatenate([ogp.grad_complex_step(spec, p[s * group:(s + 1) * group], t, Y[s], DY[s]) for s in range(S)])
+    assert_grad_close(g, ref)
+
+
+def test_scan_gradient_status_and_bounds():
+    t, y, dy, _ = fake_lightcurve(100, 35)
+    kernel, _ = build("drw+lor")
+    gp = GP(kernel, mean=float(np.mean(y)))
+    gp.compute(t, dy + 1e-12)
+    p = np.tile(gp.get_parameter_vector(), (2, 1)); p[1, 0] = 31.0
+    ll, g, st = gp.grad_log_likelihood_batch(y, p, apply_prior=True, return_status=True, kernel="scan")
+    assert st[1] == 3 and ll[1] == -np.inf and np.all(g[1] == 0.0) and np.all(np.isfinite(g[0]))
+    # a model wider than 4 state dimensions is not covered: forcing the scan is an error, "auto" falls back to K2
+    k7, _ = build("3sho+real")
+    gp7 = GP(k7, mean=float(np.mean(y))); gp7.compute(t, dy + 1e-12)
+    with pytest.raises(_native.MtgError):
+        gp7.grad_log_likelihood_batch(y, gp7.get_parameter_vector()[None, :], kernel="scan")
+    ll7, g7 = gp7.grad_log_likelihood_batch(y, gp7.get_parameter_vector()[None, :])
+    assert np.isfinite(ll7[0]) and np.all(np.isfinite(g7))
