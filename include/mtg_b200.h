@@ -95,8 +95,8 @@ typedef struct mtg_model {
 /* flags for mtg_loglike_* / mtg_grad_* */
 #define MTG_FLAG_APPLY_PRIOR   1u  /* add celerite log_prior (box, BendingPowerlaw): out = -inf outside  (gpmodelling.py:147-152) */
 #define MTG_FLAG_DS_MEAN       2u  /* residual = y - ds_mean[data set] (mean frozen at mean(y), gpmodelling.py:83-87)            */
-#define MTG_FLAG_SCAN          4u  /* mtg_loglike_*: force the parallel-in-time kernel K9 (MTG_EUNSUP if the model is not covered)  */
-#define MTG_FLAG_NO_SCAN       8u  /* mtg_loglike_*: force the one-thread-per-series kernel K1                                      */
+#define MTG_FLAG_SCAN          4u  /* force the parallel-in-time kernels: K9 (mtg_loglike_*), K11 (mtg_loglike_grad_*), K10 (mtg_ensemble_*); MTG_EUNSUP if not covered */
+#define MTG_FLAG_NO_SCAN       8u  /* force the one-thread-per-series kernels: K1, K2, K8                                           */
 
 /* ---- library / device ------------------------------------------------------------------ */
 int         mtg_version(void);
@@ -141,6 +141,13 @@ int mtg_loglike_grad_host(const mtg_model_t *model, int N, int S, int group, int
                           const double *t, const double *y_sn, const double *diag_sn, const double *ds_mean,
                           const double *params, double *out_ll, double *out_grad, int32_t *status,
                           uint32_t flags);
+
+/* 1 when the parallel-in-time gradient kernel K11 (one CTA per series: forward scan + suffix scan of the adjoint, ~30 us
+ * for <= 148 series at N = 1000 against K2's ~1.1 ms) covers `model` on series of N points -- <= 4 state dimensions and
+ * series + tape within the shared memory of an SM -- i.e. when mtg_loglike_grad_* takes it for small batches
+ * (MTG_FLAG_SCAN / MTG_FLAG_NO_SCAN force either kernel) and mtg_lbfgs_* runs the tail of a batch, or a whole small
+ * batch, in its persistent kernel.  0 otherwise (K2 serves). */
+int mtg_scan_grad_supported(const mtg_model_t *model, int N);
 
 /* ---- K4: batched box-constrained L-BFGS maximum-likelihood fits -------------------------
  * Replaces scipy.optimize.minimize(_neg_log_like, x0, method="L-BFGS-B", bounds=...) of

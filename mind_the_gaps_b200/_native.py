@@ -88,6 +88,7 @@ SIGNATURES = {
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),
     "mtg_loglike_grad_host": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32]),
+    "mtg_scan_grad_supported": (ctypes.c_int, [_mp, ctypes.c_int]),
     "mtg_lbfgs_dev": (ctypes.c_int, [_mp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(MtgLbfgsOpts),
                                      _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),

@@ -11,6 +11,15 @@
 //       tests, new two-loop direction with a projected-gradient active set) or shrink the step.
 // The host only launches rounds and reads the active count every few rounds.
 //
+// TAIL: a K2 round costs ~1.1 ms at N = 1000 whatever the batch, and most rounds of a batched fit serve a few hundred slowly
+// converging problems.  Once the active count drops below MTG_LBFGS_SWITCH (default: about what makes one pass of the
+// persistent kernel over the active problems as cheap as one K2 round) the remaining problems are handed to ONE launch of
+// k_lbfgs_persist: every CTA takes a problem from a work queue, copies its optimiser state into shared memory and
+// runs its whole remaining L-BFGS loop there -- gradient by the parallel-in-time kernel K11 (series_loglike_grad, ~30 us),
+// update by thread 0 with the same state machine (lbfgs_advance) -- then writes the state back and takes the next one.
+// No rounds, no compaction, no host synchronisation, and stragglers no longer hold the batch.  Small batches
+// (GPModelling.fit on one lightcurve) run entirely in this kernel.
+//
 // Differences from scipy's L-BFGS-B (Byrd-Lu-Nocedal-Zhu): the generalised-Cauchy-point /
 // subspace-minimisation step is replaced by a projected L-BFGS direction (variables at a bound with
 // the gradient pointing outwards are frozen for the iteration) and the More-Thuente line search by
@@ -20,7 +29,7 @@
 // iterations, and every straggler costs the whole batch one latency-bound round) and cautious (s.y > 0) updates.  Stopping tests
 // are scipy's: projected-gradient inf-norm <= gtol, relative decrease <= ftol.  Gradients are
 // analytic (K2) instead of 2-point finite differences.
-#include "mtg_common.cuh"
+#include "mtg_scan_grad.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_select.cuh>
@@ -132,12 +141,10 @@ __device__ __forceinline__ void lbfgs_set_trial(const LbfgsState &s, const Lbfgs
         s.XT[(size_t)b * nd + k] = clampd(s.X[(size_t)k * B + b] + alpha * s.Dir[(size_t)k * B + b], p.lo[k], p.hi[k]);
 }
 
-__global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__restrict__ list,
-                               const int32_t *__restrict__ count)
+// one transition of problem b's state machine after its trial point was evaluated (LL, GT, k2_status hold the result);
+// returns true when the problem is finished (status / flags written)
+__device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count) return;
-    const int b = list[i];
     const int nd = p.nd, B = s.B;
     double ft = -s.LL[b];
     if (s.k2_status[b] != 0 || !isfinite(ft)) ft = INFINITY;
@@ -243,6 +250,143 @@ __global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__res
         else { s.ls_count[b] = 0; s.n_exp[b] = 0; s.has_cand[b] = 0; lbfgs_set_trial(s, p, b, alpha); }
     }
     if (done) { s.status[b] = status; s.flags[b] = 0; }
+    return done;
+}
+
+__global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__restrict__ list,
+                               const int32_t *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    lbfgs_advance(s, p, list[i]);
+}
+
+// ---- the persistent tail kernel -------------------------------------------------------------------------------------------
+// per-problem optimiser state in shared memory: the same SoA arrays with B = 1
+struct LbfgsLocal {
+    double X[MTG_MAX_PARAMS], G[MTG_MAX_PARAMS], Dir[MTG_MAX_PARAMS];
+    double SH[LB_MAXM * MTG_MAX_PARAMS], YH[LB_MAXM * MTG_MAX_PARAMS], RHO[LB_MAXM];
+    double F, alpha, gd;
+    double XT[MTG_MAX_PARAMS], GT[MTG_MAX_PARAMS], LL;
+    double XC[MTG_MAX_PARAMS], GC[MTG_MAX_PARAMS], FC;
+    int32_t hist_n, hist_head, ls_count, iter, phase, status, restarted, k2_status, flags, has_cand, n_exp;
+};
+
+template <int JR, int JC, bool DUAL>
+__global__ void __launch_bounds__(K9_THREADS, 1)
+k_lbfgs_persist(const __grid_constant__ Plan pl, const BatchArgs a, const LbfgsState s, const __grid_constant__ LbfgsParams p,
+                const int32_t *__restrict__ list, const int32_t *__restrict__ count, int32_t *cursor, long long max_rounds)
+{
+    constexpr int J = JR + 2 * JC;
+    __shared__ k9::Scratch<J> sc;
+    __shared__ k9::GScratch<JR, JC, DUAL> gs;
+    __shared__ LbfgsLocal loc;
+    __shared__ int cur, done_flag;
+    extern __shared__ double lb_dyn[];               // [3][N] series, then K11's tape
+    double *series = lb_dyn, *tape = lb_dyn + 3 * (size_t)a.N;
+    const int tid = threadIdx.x, T = blockDim.x, nd = p.nd, m = s.m;
+    const size_t B = (size_t)s.B;
+    const bool dsm = (a.flags & MTG_FLAG_DS_MEAN) != 0;
+    LbfgsState ls = s;
+    ls.B = 1;
+    ls.X = loc.X; ls.G = loc.G; ls.Dir = loc.Dir; ls.SH = loc.SH; ls.YH = loc.YH; ls.RHO = loc.RHO;
+    ls.F = &loc.F; ls.alpha = &loc.alpha; ls.gd = &loc.gd; ls.XT = loc.XT; ls.GT = loc.GT; ls.LL = &loc.LL;
+    ls.XC = loc.XC; ls.GC = loc.GC; ls.FC = &loc.FC;
+    ls.hist_n = &loc.hist_n; ls.hist_head = &loc.hist_head; ls.ls_count = &loc.ls_count; ls.iter = &loc.iter; ls.phase = &loc.phase;
+    ls.status = &loc.status; ls.restarted = &loc.restarted; ls.k2_status = &loc.k2_status; ls.flags = &loc.flags;
+    ls.has_cand = &loc.has_cand; ls.n_exp = &loc.n_exp;
+    int staged_ds = -1;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { const int i = atomicAdd(cursor, 1); cur = i < *count ? list[i] : -1; }
+        __syncthreads();
+        const int b = cur;
+        if (b < 0) break;
+        // ---- state in ----
+        for (int k = tid; k < nd; k += T) {
+            loc.X[k] = s.X[k * B + b]; loc.G[k] = s.G[k * B + b]; loc.Dir[k] = s.Dir[k * B + b];
+            loc.XC[k] = s.XC[k * B + b]; loc.GC[k] = s.GC[k * B + b];
+            loc.XT[k] = s.XT[(size_t)b * nd + k];
+        }
+        for (int k = tid; k < m * nd; k += T) { loc.SH[k] = s.SH[k * B + b]; loc.YH[k] = s.YH[k * B + b]; }
+        for (int k = tid; k < m; k += T) loc.RHO[k] = s.RHO[k * B + b];
+        if (tid == 0) {
+            loc.F = s.F[b]; loc.alpha = s.alpha[b]; loc.gd = s.gd[b]; loc.FC = s.FC[b];
+            loc.hist_n = s.hist_n[b]; loc.hist_head = s.hist_head[b]; loc.ls_count = s.ls_count[b]; loc.iter = s.iter[b];
+            loc.phase = s.phase[b]; loc.status = s.status[b]; loc.restarted = s.restarted[b]; loc.flags = s.flags[b];
+            loc.has_cand = s.has_cand[b]; loc.n_exp = s.n_exp[b];
+        }
+        const int ds = b / a.group;
+        if (ds != staged_ds) { k9::stage_series(series, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S); staged_ds = ds; }
+        else __syncthreads();
+        const double dsv = dsm ? a.ds_mean[ds] : 0.0;
+        // ---- the problem's remaining L-BFGS loop ----
+        for (long long round = 0; round < max_rounds; ++round) {
+            int st;
+            const double ll = k9::series_loglike_grad<JR, JC, DUAL>(pl, loc.XT, a.N, series, series + a.N, series + 2 * a.N, dsm, dsv,
+                                                                    sc, gs, tape, &st, loc.GT);
+            if (tid == 0) {
+                loc.LL = ll; loc.k2_status = st;
+                done_flag = lbfgs_advance(ls, p, 0) ? 1 : 0;
+            }
+            __syncthreads();
+            if (done_flag) break;
+        }
+        // ---- state out ----
+        for (int k = tid; k < nd; k += T) {
+            s.X[k * B + b] = loc.X[k]; s.G[k * B + b] = loc.G[k]; s.Dir[k * B + b] = loc.Dir[k];
+            s.XC[k * B + b] = loc.XC[k]; s.GC[k * B + b] = loc.GC[k];
+            s.XT[(size_t)b * nd + k] = loc.XT[k];
+        }
+        for (int k = tid; k < m * nd; k += T) { s.SH[k * B + b] = loc.SH[k]; s.YH[k * B + b] = loc.YH[k]; }
+        for (int k = tid; k < m; k += T) s.RHO[k * B + b] = loc.RHO[k];
+        if (tid == 0) {
+            s.F[b] = loc.F; s.alpha[b] = loc.alpha; s.gd[b] = loc.gd; s.FC[b] = loc.FC;
+            s.hist_n[b] = loc.hist_n; s.hist_head[b] = loc.hist_head; s.ls_count[b] = loc.ls_count; s.iter[b] = loc.iter;
+            s.phase[b] = loc.phase; s.status[b] = loc.status; s.restarted[b] = loc.restarted; s.flags[b] = loc.flags;
+            s.has_cand[b] = loc.has_cand; s.n_exp[b] = loc.n_exp;
+        }
+    }
+}
+
+template <int JR, int JC, bool DUAL>
+static int launch_persist_one(const Plan &pl, const BatchArgs &a, const LbfgsState &s, const LbfgsParams &p, const int32_t *list,
+                              const int32_t *count, int32_t *cursor, int bound, long long max_rounds, cudaStream_t stream)
+{
+    const size_t dyn = mtg_k11_smem_bytes(pl, a.N);
+    auto kern = k_lbfgs_persist<JR, JC, DUAL>;
+    MTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = bound < sms ? bound : sms;
+    MTG_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t), stream));
+    kern<<<grid, K9_THREADS, dyn, stream>>>(pl, a, s, p, list, count, cursor, max_rounds);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k_lbfgs_persist launch");
+}
+template <int JR, int JC>
+static int launch_persist(const Plan &pl, const BatchArgs &a, const LbfgsState &s, const LbfgsParams &p, const int32_t *list,
+                          const int32_t *count, int32_t *cursor, int bound, long long max_rounds, cudaStream_t stream)
+{
+    if (pl.has_sho) return launch_persist_one<JR, JC, true>(pl, a, s, p, list, count, cursor, bound, max_rounds, stream);
+    return launch_persist_one<JR, JC, false>(pl, a, s, p, list, count, cursor, bound, max_rounds, stream);
+}
+#define LBP_CASE(R, C) if (pl.jr == R && pl.jc == C) return launch_persist<R, C>(pl, a, s, p, list, count, cursor, bound, max_rounds, stream);
+static int persist_dispatch(const Plan &pl, const BatchArgs &a, const LbfgsState &s, const LbfgsParams &p, const int32_t *list,
+                            const int32_t *count, int32_t *cursor, int bound, long long max_rounds, cudaStream_t stream)
+{
+    LBP_CASE(1, 0) LBP_CASE(2, 0) LBP_CASE(3, 0) LBP_CASE(0, 1) LBP_CASE(1, 1) LBP_CASE(2, 1) LBP_CASE(0, 2)
+    mtg_set_error("persistent L-BFGS: unsupported kernel structure: %d real + %d complex slots", pl.jr, pl.jc);
+    return MTG_EUNSUP;
+}
+
+// active count at and below which the remaining problems go to the persistent kernel (0 disables it)
+static int lbfgs_switch_count()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MTG_LBFGS_SWITCH"); v = e ? atoi(e) : 4096; }
+    return v;
 }
 
 __global__ void k_lbfgs_finish(LbfgsState s, double *__restrict__ out_x, double *__restrict__ out_nll,
@@ -312,7 +456,7 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     s.phase = take_i(Bz); s.status = take_i(Bz); s.restarted = take_i(Bz); s.k2_status = take_i(Bz); s.flags = take_i(Bz);
     s.has_cand = take_i(Bz); s.n_exp = take_i(Bz);
     int32_t *list_a = take_i(Bz), *list_b = take_i(Bz);
-    int32_t *d_count = take_i(8);           // [0], [1]: ping-pong counts
+    int32_t *d_count = take_i(8);           // [0], [1]: ping-pong counts, [4]: work-queue cursor of the persistent kernel
     void *cub_tmp = (void *)(((uintptr_t)iptr + 255) & ~(uintptr_t)255);
 
     const int chunk = mtg_k2_chunk(pl, N, B);
@@ -339,8 +483,15 @@ extern "C" int mtg_lbfgs_dev(const mtg_model_t *model, int N, int S, int group, 
     int32_t *cnt = d_count, *cnt_next = d_count + 1;
     const long long max_rounds = (long long)p.max_iter * (p.max_ls + LB_MAX_EXPAND + 1) + 2;
     rc = 0;
+    const bool can_persist = lbfgs_switch_count() > 0 && mtg_k11_supports(pl, N) && N >= 64;
     for (long long round = 0; round < max_rounds && bound > 0; ++round) {
         BatchArgs a{N, S, group, bound, t, y, diag, ds_mean, s.XT, s.LL, s.GT, s.k2_status, flags, list, cnt, nullptr};
+        if (can_persist && bound <= lbfgs_switch_count()) {
+            // the tail (or a small batch from its first evaluation on): one launch runs every remaining problem to completion
+            if (debug) fprintf(stderr, "[mtg_lbfgs] B=%d round %lld: %d active -> persistent kernel\n", B, round, bound);
+            rc = persist_dispatch(pl, a, s, p, list, cnt, d_count + 4, bound, max_rounds - round, stream);
+            break;
+        }
         if ((rc = mtg_k2_run(pl, a, tape, chunk, stream))) break;
         k_lbfgs_update<<<(bound + LB_THREADS - 1) / LB_THREADS, blk, 0, stream>>>(s, p, list, cnt);
         // ordered compaction of the still-active problems

@@ -101,3 +101,10 @@ long long mtg_scan_grad_max_batch()
     if (v < 0) { const char *e = getenv("MTG_SCAN_GRAD_MAX_B"); v = e ? atoll(e) : 4096; }
     return v;
 }
+
+extern "C" int mtg_scan_grad_supported(const mtg_model_t *model, int N)
+{
+    Plan pl;
+    if (!model || mtg_build_plan(model, &pl)) return 0;
+    return mtg_k11_supports(pl, N) ? 1 : 0;
+}

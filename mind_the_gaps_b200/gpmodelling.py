@@ -5,8 +5,9 @@ Same constructor, methods, keyword arguments, properties and error behaviour as 
 class.  What changed underneath:
 
 * ``self.gp`` is ``mind_the_gaps_b200.celerite.GP`` (K1/K2 kernels) instead of ``celerite.GP``;
-* ``fit`` is the reference's scipy L-BFGS-B call with every finite-difference gradient done as one batched launch
-  (``optimizer="device"``: the batched device L-BFGS with analytic gradients the LRT driver uses for thousands of fits);
+* ``fit`` runs the device L-BFGS with analytic gradients (one launch of the persistent kernel for a single lightcurve;
+  the same optimiser fits the thousands of simulated lightcurves of the LRT); ``optimizer="scipy"`` keeps the reference's
+  scipy L-BFGS-B call with every finite-difference gradient request done as one batched launch;
 * ``derive_posteriors`` runs emcee's stretch-move loop inside ONE kernel launch per convergence interval
   (``sampler.DeviceEnsembleSampler``: kernel K10 for the one-lightcurve case, K8 for thousands of ensembles;
   ``device_sampler=False`` keeps the host loop with one batched launch per half step) -- ``cores`` is accepted and
@@ -14,12 +15,13 @@ class.  What changed underneath:
 * ``generate_from_posteriors`` simulates all ``nsims`` lightcurves in one batched device call
   (``cpus`` accepted and ignored).
 """
+import ctypes
 import warnings
 
 import numpy as np
 from scipy.optimize import OptimizeResult
 
-from . import fitting
+from . import _native, fitting
 from .celerite import GP
 from .celerite.modeling import ConstantModel
 from .lightcurves import GappyLightcurve
@@ -90,14 +92,19 @@ class GPModelling(object):
         """Maximum-likelihood fit within ``gp.get_parameter_bounds()``; returns an ``OptimizeResult`` like
         ``scipy.optimize.minimize``.
 
-        ``optimizer="scipy"`` (the default for one start): the reference's own call -- scipy's L-BFGS-B with 2-point finite
-        differences (gpmodelling.py:192-193) -- every function-and-gradient request being one batched device launch
-        (``fitting.scipy_lbfgsb``).  ``optimizer="device"`` (the default for ``n_starts > 1``): the batched device L-BFGS
-        with analytic gradients that the LRT driver uses for thousands of lightcurves, best of the starts returned."""
+        ``optimizer="device"``: the device L-BFGS with analytic gradients that also serves the LRT -- for one lightcurve the
+        whole optimisation is ONE launch of the persistent kernel (``csrc/mtg_lbfgs.cu``: parallel-in-time gradient K11,
+        ~30 us per iteration); with ``n_starts > 1`` the best of the starts is returned.  ``optimizer="scipy"``: the
+        reference's own call -- scipy's L-BFGS-B with 2-point finite differences (gpmodelling.py:192-193) -- every
+        function-and-gradient request being one batched device launch (``fitting.scipy_lbfgsb``): same iterates as the
+        reference.  ``"auto"`` (default): the device optimiser when the parallel-in-time kernels cover the model (<= 4 state
+        dimensions, series fits an SM's shared memory) or ``n_starts > 1``, scipy otherwise."""
         if initial_params is None:
             initial_params = self.initial_params
         if optimizer == "auto":
-            optimizer = "scipy" if int(n_starts) <= 1 else "device"
+            lib = _native.lib()
+            scan_ok = lib.mtg_device_count() > 0 and bool(lib.mtg_scan_grad_supported(ctypes.byref(self.gp.device_model()), int(self._lightcurve.n)))
+            optimizer = "device" if (scan_ok or int(n_starts) > 1) else "scipy"
         if optimizer not in ("scipy", "device"):
             raise ValueError("optimizer must be 'auto', 'scipy' or 'device'")
         lc = self._lightcurve
