@@ -264,9 +264,9 @@ def c5_measurement(torch, lib, _native, dev, stream, timed, rank, world, n_point
             "status_counts": [int(x) for x in torch.bincount(st, minlength=4).tolist()]}
 
 
-def c3_measurement(torch, rank, world, n_lc=10000, n_e13=64):
-    """Simulator ensemble on the 1000-point gapped window: n_lc TK95 lightcurves + Poisson noise over the ranks, and a
-    bounded E13 (lognormal) + Kraft sample."""
+def c3_measurement(torch, rank, world, n_lc=10000, n_e13=10000, e13_budget_s=60.0):
+    """Simulator ensemble on the 1000-point gapped window (config C3): n_lc TK95 (Gaussian) lightcurves + Poisson noise and
+    n_e13 log-normal (E13) lightcurves + Kraft noise, both sharded over the ranks."""
     from mind_the_gaps_b200.lightcurves import GappyLightcurve
     from mind_the_gaps_b200.models import psd_models
     from helpers import window
@@ -288,63 +288,125 @@ def c3_measurement(torch, rank, world, n_lc=10000, n_e13=64):
                                        "algorithmic_GBps": mine * (24.0 * n_fft + 8.0 * n_fft / 2) / wall / 1e9,
                                        "finite": bool(np.all(np.isfinite(noisy)))}
         sim.close()
+    # config C3 proper: 10^4 LOG-NORMAL (Emmanoulopoulos et al. 2013 PDF adjustment) lightcurves with Kraft noise, sharded over
+    # the ranks, generated chunk by chunk; bounded by a time budget so the default bench always finishes (the count
+    # actually done is reported and the rate is measured, never extrapolated).
     lc2 = GappyLightcurve(tt_, np.full(N_POINTS, 0.01), np.full(N_POINTS, 0.002), exposures, bkg_rate=np.full(N_POINTS, 0.001),
                           bkg_rate_err=np.full(N_POINTS, 1e-4))
     psd2 = psd_models.BendingPowerlaw(S0=(0.3 * 0.01) ** 2, omega0=2 * np.pi / (20 * day))
-    sim = lc2.get_simulator(psd2, "Lognormal", extension_factor=2, fft_length="fast", max_iter=400)
     import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        sim.generate_lightcurves(4, seed=1)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        rates, info = sim.generate_lightcurves(n_e13, seed=4, return_info=True)
-        noisy, dy = sim.add_noise(rates, seed=5)
-        torch.cuda.synchronize(); wall = time.perf_counter() - t0
-    out["e13_lognormal_kraft_fast"] = {"lightcurves": n_e13, "wall_s": wall, "lightcurves_per_s_per_gpu": n_e13 / wall,
-                                       "e13_iterations_mean": float(np.mean(info["e13_iterations"])), "noise": sim.noise.name,
-                                       "finite": bool(np.all(np.isfinite(noisy)))}
+    for mode in ("exact",):
+        sim = lc2.get_simulator(psd2, "Lognormal", extension_factor=2, fft_length=mode, max_iter=400)
+        target = -(-n_e13 // world)
+        chunk = 128
+        done, its, finite = 0, [], True
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim.generate_lightcurves(4, seed=1)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            while done < target and time.perf_counter() - t0 < e13_budget_s:
+                n = min(chunk, target - done)
+                rates, info = sim.generate_lightcurves(n, seed=4 + done + 1000003 * rank, return_info=True)
+                noisy, dy = sim.add_noise(rates, seed=5 + done)
+                its.append(info["e13_iterations"]); finite = finite and bool(np.all(np.isfinite(noisy)))
+                done += n
+            torch.cuda.synchronize(); wall = time.perf_counter() - t0
+        out["e13_lognormal_kraft_" + mode] = {"lightcurves_target_per_gpu": target, "lightcurves_done_per_gpu": done, "completed": done >= target,
+                                              "wall_s": wall, "lightcurves_per_s_per_gpu": done / wall,
+                                              "seconds_for_target_at_this_rate": target * wall / max(done, 1),
+                                              "e13_iterations_mean": float(np.mean(np.concatenate(its))) if its else None,
+                                              "n_fft": int(sim.fftndatapoints), "noise": sim.noise.name, "finite": finite,
+                                              "time_budget_s": e13_budget_s}
     sim.close()
     return out
 
 
-def cpu_lrt_rate(n_sims=2):
-    """The reference's LRT algorithm on ONE host core (tutorial_ppp.ipynb cells 11-15 without the MCMC refinement, i.e.
-    flattering to the CPU): numpy TK95 + binning + Poisson noise (oracle.simulator), then scipy L-BFGS-B with
-    finite-difference gradients (as GPModelling.fit) on the C restatement of celerite, null (1 start) and alternative (1 start)."""
+def _cpu_lrt_one(job):
+    """One simulation of the reference's LRT procedure on ONE host core (tutorial_ppp.ipynb cells 11-15): numpy TK95 +
+    binning + Poisson noise (oracle.simulator), then per model scipy L-BFGS-B with finite-difference gradients (as
+    GPModelling.fit) on the C restatement of celerite -- and, when ``refine``, the notebook's 30 walkers x 500 steps of the
+    stretch move (oracle.sampler on the same C likelihood) whose best log-probability is kept.  Returns
+    (T, likelihood evaluations, seconds)."""
+    seed, refine = job
+    os.environ["OMP_NUM_THREADS"] = "1"
     from scipy.optimize import minimize
-    from oracle import cref, simulator as osim, terms as oterms
+    from oracle import cref, sampler as osamp, simulator as osim, terms as oterms
     from helpers import c2_truth, window
+    t0 = time.perf_counter()
     tt_, exposures = window(N_POINTS, 2)
     tr = c2_truth()
     cfg = osim.setup(tt_, exposures, aliasing_factor=2, extension_factor=2)
-    rng = np.random.default_rng(11)
+    rng = np.random.default_rng(1000 + seed)
     M = cfg["n_fft"] // 2 + 1
     psd = lambda w: oterms.psd([("drw",)], tr[:2], w)
-    t0 = time.perf_counter()
+    re, im = rng.normal(size=(2, M))
+    full = osim.simulate_regular(cfg["n_fft"], cfg["sim_dt"], psd, 0.5, re, im)
+    i0, i1, shift = osim.cut_segment(cfg["grid"], cfg["sim_dt"], cfg["sim_duration"], cfg["strategy"][0][0], rng.random())
+    tseg = cfg["grid"][i0:i1] + shift
+    lo = np.searchsorted(tseg, [s[0] for s in cfg["strategy"]]); hi = np.searchsorted(tseg, [s[1] for s in cfg["strategy"]])
+    rates = np.array([full[i0 + a:i0 + b].mean() for a, b in zip(lo, hi)])          # same bins as the reference's O(N N_seg) mask loop
+    counts = rng.poisson(np.clip(rates, 0, None) * exposures)
+    y, dy = osim.poisson_noise(rates, exposures, np.zeros(N_POINTS), np.zeros(N_POINTS), counts)
+    dy = np.maximum(dy, 1e-6)
     evals = 0
-    for _ in range(n_sims):
-        re, im = rng.normal(size=(2, M))
-        full = osim.simulate_regular(cfg["n_fft"], cfg["sim_dt"], psd, 0.5, re, im)
-        i0, i1, shift = osim.cut_segment(cfg["grid"], cfg["sim_dt"], cfg["sim_duration"], cfg["strategy"][0][0], rng.random())
-        tseg = cfg["grid"][i0:i1] + shift
-        lo = np.searchsorted(tseg, [s[0] for s in cfg["strategy"]]); hi = np.searchsorted(tseg, [s[1] for s in cfg["strategy"]])
-        rates = np.array([full[i0 + a:i0 + b].mean() for a, b in zip(lo, hi)])          # same bins as the reference's O(N N_seg) mask loop
-        counts = rng.poisson(np.clip(rates, 0, None) * exposures)
-        y, dy = osim.poisson_noise(rates, exposures, np.zeros(N_POINTS), np.zeros(N_POINTS), counts)
-        dy = np.maximum(dy, 1e-6)
-        for spec, x0, bounds in (([("drw",)], tr[:2], [(-15, 5), (-20, -5)]),
-                                 ([("lorentzian",), ("drw",)], np.r_[tr[2] - 2, np.log(20.0), tr[4], tr[:2]],
-                                  [(-20, 5), (0.5, 7), (-16, -9), (-15, 5), (-20, -5)])):
-            cnt = [0]
+    best = []
+    for spec, x0, bounds in (([("drw",)], tr[:2], [(-15, 5), (-20, -5)]),
+                             ([("lorentzian",), ("drw",)], np.r_[tr[2] - 2, np.log(20.0), tr[4], tr[:2]],
+                              [(-20, 5), (0.5, 7), (-16, -9), (-15, 5), (-20, -5)])):
+        cnt = [0]
 
-            def nll(p):
-                cnt[0] += 1
-                v = -cref.loglike_params(spec, p[None, :], tt_, y, dy, nthreads=1)[0]
-                return v if np.isfinite(v) else 1e25
-            minimize(nll, x0, method="L-BFGS-B", bounds=bounds)
-            evals += cnt[0]
-    dt = time.perf_counter() - t0
-    return n_sims / dt, dt, evals / n_sims
+        def nll(p):
+            cnt[0] += 1
+            v = -cref.loglike_params(spec, p[None, :], tt_, y, dy, nthreads=1)[0]
+            return v if np.isfinite(v) else 1e25
+        sol = minimize(nll, x0, method="L-BFGS-B", bounds=bounds)
+        ll = -sol.fun
+        if refine:
+            lo_b = np.array([b[0] for b in bounds], dtype=float); hi_b = np.array([b[1] for b in bounds], dtype=float)
+            W, steps = 30, 500
+
+            def logp(X):
+                cnt[0] += len(X)
+                inside = np.all((X >= lo_b) & (X <= hi_b), axis=1)
+                out = np.full(len(X), -np.inf)
+                if np.any(inside):
+                    v = cref.loglike_params(spec, X[inside], tt_, y, dy, nthreads=1)
+                    out[inside] = np.where(np.isfinite(v), v, -np.inf)
+                return out
+            rs = np.random.RandomState(seed)
+            p0 = np.clip(sol.x[None, :] + rs.normal(size=(W, len(x0))) * 0.1 * np.abs(sol.x), lo_b, hi_b)
+            _, clp, _ = osamp.stretch_move_run(logp, p0, steps, *osamp.draws_like_emcee(rs, W, steps))
+            ll = max(ll, float(np.max(clp)))
+        evals += cnt[0]
+        best.append(ll)
+    return -2.0 * (best[0] - best[1]), evals, time.perf_counter() - t0
+
+
+def cpu_lrt_all_cores(n_plain=64, n_refined=None):
+    """The reference's LRT on ALL host cores, measured (not extrapolated): ``n_plain`` simulations without and
+    ``n_refined`` (default: one per core) with the notebook's per-simulation MCMC refinement, spread over a process pool
+    (the reference's own parallelism: multiprocessing.Pool over simulations, gpmodelling.py:511-512)."""
+    import multiprocessing as mp
+    cores = host_cores()
+    n_refined = cores if n_refined is None else n_refined
+    out = {"cores": cores}
+    ctx = mp.get_context("spawn")          # the parent holds a CUDA context: never fork it
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_lrt_one, [(10_000 + k, False) for k in range(cores)][:cores], chunksize=1)      # warm: imports, oracle build
+        for label, n, refine in (("plain", n_plain, False), ("mcmc_refined", n_refined, True)):
+            if n <= 0:
+                continue
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_lrt_one, [(k, refine) for k in range(n)], chunksize=1)
+            wall = time.perf_counter() - t0
+            T = np.array([r[0] for r in res])
+            out[label] = {"simulations": n, "wall_s": wall, "sims_per_s_all_cores": n / wall,
+                          "core_seconds_per_sim": float(np.mean([r[2] for r in res])),
+                          "likelihood_evals_per_sim": float(np.mean([r[1] for r in res])),
+                          "T_median": float(np.median(T)), "seconds_for_1e4_sims_at_this_rate": 1e4 * wall / n}
+    out["sample"] = ("%d simulations without and %d with the 30 x 500 MCMC refinement, process pool over %d cores; numpy TK95 + scipy "
+                     "L-BFGS-B (finite differences, 1 start per model) on oracle/celerite_ref.c" % (n_plain, n_refined, cores))
+    return out
 
 
 def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y, d_diag, d_p, t, y, dy, p, rank, world, args):
@@ -371,6 +433,21 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
     ms = timed(k2, 3)
     out["loglike_grad"] = {"batch": Bg, "ms": ms, "evals_per_s": Bg / (ms * 1e-3),
                            "note": "forward + segment replay into shared memory + adjoint sweep; no O(N) tape in HBM"}
+    # K11 (parallel-in-time gradient, one CTA per series) against K2 for the batch sizes the tail of a batched L-BFGS sees
+    try:
+        sg = {}
+        for Bs in (1, 148, 1184):
+            s_ll = torch.empty(Bs, dtype=torch.float64, device=dev); s_g = torch.empty((Bs, 5), dtype=torch.float64, device=dev)
+            s_st = torch.empty(Bs, dtype=torch.int32, device=dev)
+            for name, flag in (("k2", _native.FLAG_NO_SCAN), ("k11_scan", _native.FLAG_SCAN)):
+                def kg():
+                    _native.check(lib.mtg_loglike_grad_dev(ctypes.byref(model), N_POINTS, 1, Bs, Bs, d_t.data_ptr(), d_y.data_ptr(), d_diag.data_ptr(),
+                                                           None, d_p.data_ptr(), s_ll.data_ptr(), s_g.data_ptr(), s_st.data_ptr(), flag, stream.cuda_stream))
+                sg["%s_us_%d_series" % (name, Bs)] = timed(kg, 10) * 1e3
+        sg["us_148_series"] = sg["k11_scan_us_148_series"]
+        out["loglike_grad_scan"] = sg
+    except Exception as exc:
+        out["loglike_grad_scan"] = {"error": repr(exc)}
     # the 32-parameter-set half-ensemble call of a 64-walker emcee step: K1 (one thread per series: the latency of the whole
     # 1000-step chain) against K9 (parallel-in-time scan, one CTA per series: what the library picks for small batches)
     s_ll = torch.empty(32, dtype=torch.float64, device=dev); s_st = torch.empty(32, dtype=torch.int32, device=dev)
@@ -424,13 +501,18 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
             with warnings.catch_warnings():                           # warm-up of the sampler / cuFFT (first use loads the library)
                 warnings.simplefilter("ignore")
                 g.derive_posteriors(fit=False, converge=False, max_steps=6000, convergence_steps=2000, walkers=12, progress=False)
+            g.fit(g.initial_params, optimizer="scipy")
+            t0 = time.perf_counter(); sol_sp = g.fit(g.initial_params, optimizer="scipy"); fit_scipy_s = time.perf_counter() - t0
             t0 = time.perf_counter(); sol = g.fit(g.initial_params); fit_s = time.perf_counter() - t0
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 t0 = time.perf_counter()
                 g.derive_posteriors(fit=False, converge=False, max_steps=10000, convergence_steps=500, walkers=12, progress=False)
                 mc_s = time.perf_counter() - t0
-            api[label] = {"fit_ms": fit_s * 1e3, "fit_nfev": int(getattr(sol, "nfev", -1)), "fit_nit": int(sol.nit),
+            api[label] = {"fit_ms": fit_s * 1e3, "fit_nit": int(sol.nit), "fit_fun": float(sol.fun),
+                          "fit_optimizer": "device L-BFGS, one launch of the persistent kernel (GPModelling.fit default)",
+                          "fit_scipy_driven_ms": fit_scipy_s * 1e3, "fit_scipy_driven_nfev": int(getattr(sol_sp, "nfev", -1)),
+                          "fit_scipy_driven_fun": float(sol_sp.fun),
                           "derive_posteriors_steps": int(g._sampler.iteration), "derive_posteriors_s": mc_s,
                           "emcee_steps_per_s_incl_tau_checks": g._sampler.iteration / mc_s, "walkers": 12}
         api["reference_published"] = "221 / 163 emcee it/s (null / alternative, 12 walkers, Pool(15)), tutorial_ppp.ipynb:132,210"
@@ -517,9 +599,17 @@ def main():
     for _ in range(args.warmup):
         l2_flush(); step()
     torch.cuda.synchronize()
-    # FP64 FMA peak of this device, measured live (roofline denominator; not in MEASURED_PEAKS.json)
+    # FP64 FMA peak of this device, measured live (roofline denominator; not in MEASURED_PEAKS.json): the DFMA probe is
+    # repeated for ~0.6 s under the clock sampler so that the clocks the peak was measured at are recorded with it
     pk = ctypes.c_double(); pk_ms = ctypes.c_double()
-    _native.check(lib.mtg_fp64_peak_probe(ctypes.byref(pk), ctypes.byref(pk_ms)))
+    pk_sampler = ClockSampler(local_rank); pk_sampler.start(); time.sleep(0.25)
+    pk_vals = []
+    t_pk = time.perf_counter()
+    while time.perf_counter() - t_pk < 0.6 or len(pk_vals) < 3:
+        _native.check(lib.mtg_fp64_peak_probe(ctypes.byref(pk), ctypes.byref(pk_ms)))
+        pk_vals.append(pk.value)
+    peak_clocks = pk_sampler.stop()
+    pk_value = max(pk_vals)
 
     sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.3)
     launches0 = lib.mtg_launch_count()
@@ -569,7 +659,11 @@ def main():
     if rank == 0:
         value = B * world * args.steps / (total_ms * 1e-3)
         ms_per_step = total_ms / args.steps
-        achieved_tf = B * FLOPS_PER_EVAL / (ms_per_step * 1e-3) / 1e12
+        # PRIMARY roofline figure: the flops the kernel EXECUTES -- the recursion runs at J = 3 because the zero-amplitude real
+        # term the reference's Lorentzian contributes (celerite_models.py:9-15) is decoupled from every output and dropped;
+        # the J = 4 count of SURVEY.md 8(d) is kept beside it as a secondary figure
+        achieved_tf = B * FLOPS_PER_EVAL_COMPUTE / (ms_per_step * 1e-3) / 1e12
+        achieved_tf_j4 = B * FLOPS_PER_EVAL / (ms_per_step * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -592,15 +686,20 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "GP.log_likelihood_batch -> mtg_loglike_host (pinned host buffers)"},
             "gpu_launches": kernel_launches,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk.value, "unit": "TFLOP/s",
-                         "frac": achieved_tf / pk.value if pk.value else None,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk_value, "unit": "TFLOP/s",
+                         "frac": achieved_tf / pk_value if pk_value else None,
                          "traffic": 15287808 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
                          "traffic_source": "profiles/r01j_k1_ncu_full_raw.csv (ncu --set full, 378880 series: dram__bytes_read 15.29 MB, "
                                            "dram__bytes_write 0), scaled to this batch",
                          "kernel": "k1_loglike<1,1,false,true>",
-                         "flops_per_eval": FLOPS_PER_EVAL, "flops_per_eval_computed_J3": FLOPS_PER_EVAL_COMPUTE,
-                         "peak_source": "mtg_fp64_peak_probe: DFMA microbenchmark measured in this run "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "flops_per_eval": FLOPS_PER_EVAL_COMPUTE,
+                         "flops_model": "N (4 J^2 + 12 J + 5) at the J = 3 the kernel executes (SURVEY.md 8d formula)",
+                         "secondary_survey_count_J4": {"flops_per_eval": FLOPS_PER_EVAL, "achieved": achieved_tf_j4,
+                                                       "frac": achieved_tf_j4 / pk_value if pk_value else None},
+                         "peak_source": "mtg_fp64_peak_probe: DFMA microbenchmark measured in this run, best of %d repetitions "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)" % len(pk_vals),
+                         "peak_clocks": peak_clocks,
+                         "peak_nominal": "148 SMs x 64 DFMA/clk x 2 x sm_mhz",
                          "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -608,6 +707,29 @@ def main():
         }
         if not args.no_extras:
             line["extras"] = extras
+            # the secondary configurations as TOP-LEVEL keys, so that the per-N scaling record keeps them (the LRT and C3 / C5
+            # legs shard a FIXED total over the ranks: strong scaling)
+            def dig(d, *path):
+                for k in path:
+                    if not isinstance(d, dict) or k not in d:
+                        return None
+                    d = d[k]
+                return d
+            line["lrt_sims_per_s"] = dig(extras, "lrt", "sims_per_s")
+            line["lrt_wall_s"] = dig(extras, "lrt", "wall_s")
+            line["lrt_fast_grid_wall_s"] = dig(extras, "lrt", "fft_length", "fast", "wall_s")
+            line["lrt_refined_wall_s"] = dig(extras, "lrt", "mcmc_refined", "wall_s")
+            line["lrt_fit_alt_ms_rank0"] = dig(extras, "lrt", "fft_length", "exact", "rank0_stage_ms", "fit_alt_ms")
+            line["lrt_fit_null_ms_rank0"] = dig(extras, "lrt", "fft_length", "exact", "rank0_stage_ms", "fit_null_ms")
+            line["lrt_simulate_ms_rank0"] = dig(extras, "lrt", "fft_length", "exact", "rank0_stage_ms", "simulate_ms")
+            line["c3_tk95_lc_per_s"] = (dig(extras, "c3_simulator", "tk95_poisson_exact", "lightcurves_per_s_per_gpu") or 0) * world or None
+            line["c3_lognormal_lc_per_s"] = (dig(extras, "c3_simulator", "e13_lognormal_kraft_exact", "lightcurves_per_s_per_gpu") or 0) * world or None
+            line["c3_lognormal_completed"] = dig(extras, "c3_simulator", "e13_lognormal_kraft_exact", "completed")
+            c5_tf = dig(extras, "c5_long_baseline_sweep", "tflops_algorithmic_per_gpu")
+            line["c5_frac"] = (c5_tf / pk_value) if (c5_tf and pk_value) else None
+            line["c5_evals_per_s"] = (dig(extras, "c5_long_baseline_sweep", "evals_per_s_per_gpu") or 0) * world or None
+            line["grad_scan_us_148_series"] = dig(extras, "loglike_grad_scan", "us_148_series")
+            line["fit_one_lightcurve_ms"] = dig(extras, "gpmodelling_public_api_one_lightcurve", "null_DRW", "fit_ms")
         if not args.no_cpu_baseline and world == 1:
             rate, n, dt, cores = cpu_port_rate(B, seconds=10.0)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
@@ -615,11 +737,7 @@ def main():
                                               "(C restatement of celerite, OpenMP)" % (n, dt)}
             if not args.no_extras:
                 try:
-                    r1, dt1, ev = cpu_lrt_rate(2)
-                    line["cpu_baseline"]["lrt"] = {"sims_per_s_one_core": r1, "sims_per_s_all_cores_if_perfectly_parallel": r1 * cores,
-                                                   "cores": cores, "sample": "2 simulations in %.1f s on one core: numpy TK95 + scipy L-BFGS-B "
-                                                   "(finite differences, 1 start per model, no MCMC refinement) on oracle/celerite_ref.c; "
-                                                   "%.0f likelihood evaluations per simulation" % (dt1, ev)}
+                    line["cpu_baseline"]["lrt"] = cpu_lrt_all_cores()
                 except Exception as exc:
                     line["cpu_baseline"]["lrt"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)

@@ -89,7 +89,8 @@ def test_lrt_driver_null_distribution():
                                return_lightcurves=True)
     assert res.T.shape == (96,) and np.all(np.isfinite(res.T))
     assert np.all(res.T > -1e-4)                      # nested start: the alternative never fits worse
-    assert 0.2 < np.median(res.T) < 12.0 and np.percentile(res.T, 95) < 40.0
+    # level pinned in tests/test_lrt_null_gpu.py (CPU refits from the same starts; look-elsewhere effect over log_omega0)
+    assert 3.0 < np.median(res.T) < 11.0 and np.percentile(res.T, 95) < 30.0
     # the recorded likelihoods are the oracle's at the recorded optima, on the simulated data
     Y, DY = res.lightcurves
     for i in (0, 17, 95):
