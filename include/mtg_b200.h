@@ -64,7 +64,15 @@ enum mtg_term_kind {
     MTG_TERM_DRW = 6,         /* log_S0, log_omega0                 -> real (S0, w0)                   */
     MTG_TERM_LORENTZIAN = 7,  /* log_S0, log_Q, log_omega0          -> complex (S0,0,w0/2Q,w0) + real (0,0) */
     MTG_TERM_COSINUS = 8,     /* log_S0, log_omega0                 -> complex (S0, 0, 0, w0)          */
-    MTG_TERM_BENDINGPL = 9    /* log_S0, log_Q, log_omega0          -> complex (S0, Q, w0, w0); prior -inf if log_S0 < log_Q */
+    MTG_TERM_BENDINGPL = 9,   /* log_S0, log_Q, log_omega0          -> complex (S0, Q, w0, w0); prior -inf if log_S0 < log_Q */
+    /* RAW terms: the "parameters" ARE celerite coefficients, evaluated by the caller.  This is the entry for user-defined
+     * celerite.terms.Term subclasses (arbitrary Python get_real_coefficients / get_complex_coefficients -- the reference's
+     * own kernels are such subclasses, mind_the_gaps/models/celerite_models.py:7-90): the host evaluates the coefficient
+     * map once per parameter set and hands the library params[B][n] = the concatenated coefficients.
+     * Gradients come back with respect to the coefficients. */
+    MTG_TERM_RAW_REAL = 10,   /* a, c                               -> real (a, c)                      */
+    MTG_TERM_RAW_COMPLEX = 11,/* a, b, c, d                         -> complex (a, b, c, d)             */
+    MTG_TERM_RAW_JITTER = 12  /* sigma^2                            -> diagonal                         */
 };
 
 /* Mean models (mind_the_gaps/gpmodelling.py:62-124, models/mean_models.py:6-31). */

@@ -69,8 +69,10 @@ class GP(ModelSet):
             kind = term._mtg_kind
             if kind is None:
                 raise NotImplementedError(
-                    "%s has no device coefficient map: only the celerite terms and the mind_the_gaps kernel "
-                    "models are supported on the GPU path (there is no CPU fallback)" % type(term).__name__)
+                    "%s has no device coefficient map (a user-defined Term): its likelihood runs on the GPU through the "
+                    "raw-coefficient entry -- GP.log_likelihood(_batch) / log_probability_batch, GPModelling.fit and the host "
+                    "sampler -- but the device-resident optimiser, sampler, predict and LRT need one of the built-in terms"
+                    % type(term).__name__)
             m.kind[k] = int(kind)
             m.extra[k] = float(term._mtg_extra)
             for i in range(term.full_size):
@@ -115,6 +117,87 @@ class GP(ModelSet):
         m.n_free = kfree
         return m
 
+    # -- user-defined terms: coefficient map on the host, everything else on the device --------------------------
+    def needs_host_coefficients(self):
+        """True when a kernel term has no device coefficient map: a user subclass of ``Term`` with its own
+        ``get_real_coefficients`` / ``get_complex_coefficients`` (the reference's kernels are written this way,
+        models/celerite_models.py:7-90).  Its coefficients are then evaluated in Python once per parameter set and the
+        likelihood runs on the device from them (``MTG_TERM_RAW_*``)."""
+        return any(t._mtg_kind is None for t in self.kernel.terms)
+
+    def _raw_model_and_rows(self, params):
+        """``(mtg_model_t of raw terms, rows (B, n_raw))`` for the parameter vectors ``params (B, ndim)``: each row holds the
+        celerite coefficients of the kernel at that parameter vector -- (a, c) per real term, (a, b, c, d) per complex
+        term, the jitter -- followed by the free mean parameters.  Degenerate real terms (a = c = 0, what the reference's
+        ``Lorentzian`` returns) are dropped: they cannot influence the likelihood."""
+        keep = self.get_parameter_vector()
+        nk = self.kernel.vector_size
+        rows, layout = [], None
+        try:
+            for row in params:
+                self.set_parameter_vector(row)
+                ar, cr, ac, bc, cc, dc = self.kernel.get_all_coefficients()
+                live = ~((ar == 0.0) & (cr == 0.0))
+                lay = (tuple(live), len(ac))
+                if layout is None:
+                    layout = lay
+                elif lay != layout:
+                    raise ValueError("the number of real / complex celerite terms changes with the parameters: not supported "
+                                     "for user-defined terms")
+                rows.append(np.concatenate([np.column_stack([ar[live], cr[live]]).ravel(), np.column_stack([ac, bc, cc, dc]).ravel(),
+                                            [self.kernel.jitter], row[nk:]]))
+        finally:
+            self.set_parameter_vector(keep)
+        n_r, n_c = int(np.sum(layout[0])), layout[1]
+        if n_r + n_c + 1 > _native.MTG_MAX_TERMS:
+            raise ValueError("at most %d celerite terms are supported" % (_native.MTG_MAX_TERMS - 1))
+        m = _native.MtgModel()
+        m.n_terms = n_r + n_c + 1
+        off = 0
+        for k in range(n_r):
+            m.kind[k] = 10; m.pidx[k][0] = off; m.pidx[k][1] = off + 1; off += 2                      # MTG_TERM_RAW_REAL
+        for k in range(n_r, n_r + n_c):
+            m.kind[k] = 11                                                                               # MTG_TERM_RAW_COMPLEX
+            for i in range(4):
+                m.pidx[k][i] = off + i
+            off += 4
+        m.kind[n_r + n_c] = 12; m.pidx[n_r + n_c][0] = off; off += 1                                     # MTG_TERM_RAW_JITTER
+        n_coef = off
+        # mean model: the free mean parameters follow the coefficients in the rows, the frozen ones keep their values
+        mean = self.mean
+        mk = None
+        for cls in type(mean).__mro__:
+            if cls.__name__ in _MEAN_KINDS:
+                mk = _MEAN_KINDS[cls.__name__]
+                break
+        if mk is None:
+            raise NotImplementedError("mean model %s is not supported on the GPU path" % type(mean).__name__)
+        m.mean_kind = mk[0]
+        names = list(mean.get_parameter_names(include_frozen=True))
+        mfull = mean.get_parameter_vector(include_frozen=True)
+        mmask = np.atleast_1d(mean.unfrozen_mask)
+        n_full = n_coef + len(names)
+        if n_full + 1 > _native.MTG_MAX_PARAMS:
+            raise ValueError("too many parameters (%d)" % n_full)
+        for i in range(n_coef):
+            m.full_default[i] = 0.0
+        for i, v in enumerate(mfull):
+            m.full_default[n_coef + i] = float(v)
+        for i, pname in enumerate(mk[1]):
+            if pname in names:
+                m.mean_pidx[i] = n_coef + names.index(pname)
+            else:                                       # GaussianModel built with 3 of its 4 names (see device_model)
+                m.mean_pidx[i] = n_full; m.full_default[n_full] = 0.0; n_full += 1
+        m.n_full = n_full
+        kfree = 0
+        for i in range(n_coef):
+            m.free_idx[kfree] = i; m.lo[kfree] = -np.inf; m.hi[kfree] = np.inf; kfree += 1
+        for i in range(len(names)):
+            if mmask[i]:
+                m.free_idx[kfree] = n_coef + i; m.lo[kfree] = -np.inf; m.hi[kfree] = np.inf; kfree += 1
+        m.n_free = kfree
+        return m, np.ascontiguousarray(rows, dtype=np.float64)
+
     # -- data -------------------------------------------------------------------------------------
     def compute(self, t, yerr=1.123e-12, check_sorted=True):
         t = np.atleast_1d(np.asarray(t, dtype=np.float64))
@@ -156,7 +239,14 @@ class GP(ModelSet):
         p = self._batch_params(params)
         B = p.shape[0]
         _native.require_device()
-        model = self.device_model()
+        if self.needs_host_coefficients():
+            if apply_prior:
+                raise ValueError("a user-defined term's prior is evaluated on the host: use log_probability_batch")
+            if B == 0:
+                return (np.empty(0), np.empty(0, dtype=np.int32)) if return_status else np.empty(0)
+            model, p = self._raw_model_and_rows(p)
+        else:
+            model = self.device_model()
         ll = out if out is not None else np.empty(B, dtype=np.float64)
         # the status array is only copied back when asked for: a device->host copy into pageable memory blocks the
         # calling thread, which would serialise the chunk pipeline of large host calls (csrc/mtg_capi.cu host_eval)
@@ -179,7 +269,7 @@ class GP(ModelSet):
         p = self._batch_params(params)
         B = p.shape[0]
         _native.require_device()
-        model = self.device_model()
+        model = self.device_model()          # raises for user-defined terms: their map to coefficients is arbitrary Python
         ll = np.empty(B, dtype=np.float64)
         grad = np.empty((B, p.shape[1]), dtype=np.float64)
         status = np.empty(B, dtype=np.int32)
@@ -198,6 +288,8 @@ class GP(ModelSet):
         inherits a device coefficient map -- makes this False, and the prior is then evaluated on the host."""
         from ..models.celerite_models import BendingPowerlaw
         from .terms import ComplexTerm, TermSum
+        if self.needs_host_coefficients():
+            return False
         known = {Model.log_prior, ModelSet.log_prior, TermSum.log_prior, ComplexTerm.log_prior, BendingPowerlaw.log_prior}
         parts = list(self.kernel.terms) + [self.kernel, self.mean]
         return all(type(m).log_prior in known for m in parts)

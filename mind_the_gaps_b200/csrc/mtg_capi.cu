@@ -69,10 +69,16 @@ int mtg_build_plan(const mtg_model_t *m, Plan *pl)
         const int *ix = m->pidx[k];
         int np = 0;
         switch (kind) {
-        case MTG_TERM_REAL: case MTG_TERM_DRW: np = 2;
+        case MTG_TERM_REAL: case MTG_TERM_DRW: case MTG_TERM_RAW_REAL: np = 2;
             if (jr >= MTG_MAXR) goto toowide;
-            pl->r_ia[jr] = ix[0]; pl->r_ic[jr] = ix[1]; ++jr; jcel += 1; break;
-        case MTG_TERM_JITTER: np = 1; pl->jit_idx[pl->n_jit++] = ix[0]; break;
+            pl->r_ia[jr] = ix[0]; pl->r_ic[jr] = ix[1]; pl->r_raw[jr] = kind == MTG_TERM_RAW_REAL; ++jr; jcel += 1; break;
+        case MTG_TERM_JITTER: case MTG_TERM_RAW_JITTER: np = 1;
+            pl->jit_raw[pl->n_jit] = kind == MTG_TERM_RAW_JITTER; pl->jit_idx[pl->n_jit++] = ix[0]; break;
+        case MTG_TERM_RAW_COMPLEX:
+            if (jc >= MTG_MAXC) goto toowide;
+            np = 4; pl->c_kind[jc] = CS_RAW; pl->c_extra[jc] = 0.0;
+            for (int i = 0; i < 4; ++i) pl->c_idx[jc][i] = ix[i];
+            ++jc; jcel += 2; break;
         case MTG_TERM_COMPLEX3: case MTG_TERM_COMPLEX4: case MTG_TERM_SHO: case MTG_TERM_MATERN32:
         case MTG_TERM_LORENTZIAN: case MTG_TERM_COSINUS: case MTG_TERM_BENDINGPL: {
             if (jc >= MTG_MAXC) goto toowide;

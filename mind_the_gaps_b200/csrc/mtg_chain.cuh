@@ -28,11 +28,11 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
 {
     auto add = [&](int full_idx, double v) { const int pos = pl.src_pos[full_idx]; if (pos >= 0) grad[pos] += v; };
     for (int k = 0; k < pl.n_jit; ++k)
-        add(pl.jit_idx[k], g.a_sum * 2.0 * exp(2.0 * plan_param(pl, x, pl.jit_idx[k])));
+        add(pl.jit_idx[k], pl.jit_raw[k] ? g.a_sum : g.a_sum * 2.0 * exp(2.0 * plan_param(pl, x, pl.jit_idx[k])));
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
-        add(pl.r_ia[j], (g.ar[j] + g.a_sum) * c.ar[j]);
-        add(pl.r_ic[j], g.cr[j] * (-c.ncr[j] * MTG_LN2));
+        add(pl.r_ia[j], (g.ar[j] + g.a_sum) * (pl.r_raw[j] ? 1.0 : c.ar[j]));
+        add(pl.r_ic[j], g.cr[j] * (pl.r_raw[j] ? 1.0 : -c.ncr[j] * MTG_LN2));
     }
 #pragma unroll
     for (int j = 0; j < JC; ++j) {
@@ -42,6 +42,7 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
         switch (pl.c_kind[j]) {
         case CS_COMPLEX3: add(ix[0], ga * a); add(ix[1], gc * cc); add(ix[2], gd * d); break;
         case CS_COMPLEX4: add(ix[0], ga * a); add(ix[1], gb * b); add(ix[2], gc * cc); add(ix[3], gd * d); break;
+        case CS_RAW: add(ix[0], ga); add(ix[1], gb); add(ix[2], gc); add(ix[3], gd); break;
         case CS_LORENTZIAN: add(ix[0], ga * a); add(ix[1], -gc * cc); add(ix[2], gc * cc + gd * d); break;
         case CS_COSINUS: add(ix[0], ga * a); add(ix[1], gd * d); break;
         case CS_BENDINGPL: add(ix[0], ga * a); add(ix[1], gb * b); add(ix[2], (gc + gd) * d); break;

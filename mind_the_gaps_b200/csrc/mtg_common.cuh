@@ -19,7 +19,7 @@
 #define MTG_MAXC 8          // complex (width-2) recursion slots
 
 // complex-slot program kinds (device side)
-enum { CS_COMPLEX3 = 0, CS_COMPLEX4, CS_SHO, CS_MATERN32, CS_LORENTZIAN, CS_COSINUS, CS_BENDINGPL };
+enum { CS_COMPLEX3 = 0, CS_COMPLEX4, CS_SHO, CS_MATERN32, CS_LORENTZIAN, CS_COSINUS, CS_BENDINGPL, CS_RAW };
 
 struct Plan {
     int32_t jr, jc;                 // recursion slots actually computed
@@ -27,10 +27,11 @@ struct Plan {
     int32_t has_sho;                // any SHO slot (can flip to two real terms when Q < 1/2)
     int32_t b_zero;                 // every complex slot has b == 0 structurally (ComplexTerm(a,c,d), Lorentzian, Cosinus)
     int32_t r_ia[MTG_MAXR], r_ic[MTG_MAXR];     // real slot: a = exp(p[ia]), c = exp(p[ic])
+    int32_t r_raw[MTG_MAXR];                    // ... or a = p[ia], c = p[ic] (MTG_TERM_RAW_REAL: coefficients supplied by the caller)
     int32_t c_kind[MTG_MAXC];
     int32_t c_idx[MTG_MAXC][4];
     double  c_extra[MTG_MAXC];
-    int32_t n_jit; int32_t jit_idx[MTG_MAX_TERMS];
+    int32_t n_jit; int32_t jit_idx[MTG_MAX_TERMS]; int32_t jit_raw[MTG_MAX_TERMS];     // jitter = exp(2 p) or p (raw)
     int32_t n_bpl; int32_t bpl_s0[MTG_MAX_TERMS], bpl_q[MTG_MAX_TERMS];   // BendingPowerlaw prior pairs
     int32_t mean_kind; int32_t mean_idx[4];
     int32_t n_full, n_free;
@@ -61,6 +62,14 @@ __device__ __forceinline__ double plan_param(const Plan &pl, const double *__res
     const int pos = pl.src_pos[i];
     return pos >= 0 ? x[pos] : pl.full_default[i];
 }
+
+// diagonal jitter of term k, amplitude / rate of real slot j
+__device__ __forceinline__ double plan_jitter(const Plan &pl, const double *__restrict__ x, int k)
+{ const double p = plan_param(pl, x, pl.jit_idx[k]); return pl.jit_raw[k] ? p : exp(2.0 * p); }
+__device__ __forceinline__ double plan_real_a(const Plan &pl, const double *__restrict__ x, int j)
+{ const double p = plan_param(pl, x, pl.r_ia[j]); return pl.r_raw[j] ? p : exp(p); }
+__device__ __forceinline__ double plan_real_c(const Plan &pl, const double *__restrict__ x, int j)
+{ const double p = plan_param(pl, x, pl.r_ic[j]); return pl.r_raw[j] ? p : exp(p); }
 
 // celerite Model.log_prior: 0 inside the closed box else -inf; the overrides the reference path can reach:
 // BendingPowerlaw (celerite_models.py:85-90) and celerite's ComplexTerm with four parameters.  Returns true when inside.
@@ -99,11 +108,11 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
                                                   Coef<JR, JC, DUAL> &c)
 {
     double a_sum = 0.0;
-    for (int k = 0; k < pl.n_jit; ++k) a_sum += exp(2.0 * plan_param(pl, x, pl.jit_idx[k]));
+    for (int k = 0; k < pl.n_jit; ++k) a_sum += plan_jitter(pl, x, k);
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
-        c.ar[j] = exp(plan_param(pl, x, pl.r_ia[j]));
-        c.ncr[j] = -exp(plan_param(pl, x, pl.r_ic[j])) * MTG_LOG2E;
+        c.ar[j] = plan_real_a(pl, x, j);
+        c.ncr[j] = -plan_real_c(pl, x, j) * MTG_LOG2E;
         a_sum += c.ar[j];
     }
 #pragma unroll
@@ -116,6 +125,7 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
         case CS_COMPLEX3: a = exp(p0); cc = exp(p1); d = exp(plan_param(pl, x, pl.c_idx[j][2])); break;
         case CS_COMPLEX4: a = exp(p0); b = exp(p1); cc = exp(plan_param(pl, x, pl.c_idx[j][2]));
                           d = exp(plan_param(pl, x, pl.c_idx[j][3])); break;
+        case CS_RAW:      a = p0; b = p1; cc = plan_param(pl, x, pl.c_idx[j][2]); d = plan_param(pl, x, pl.c_idx[j][3]); break;
         case CS_LORENTZIAN: { const double w0 = exp(plan_param(pl, x, pl.c_idx[j][2]));
                           a = exp(p0); cc = 0.5 * w0 / exp(p1); d = w0; } break;
         case CS_COSINUS:  a = exp(p0); cc = 0.0; d = exp(p1); break;

@@ -62,7 +62,7 @@ __global__ void k_predict_finish(const __grid_constant__ Plan pl, int N, const d
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double jitter = 0.0;
-    for (int k = 0; k < pl.n_jit; ++k) jitter += exp(2.0 * plan_param(pl, params, pl.jit_idx[k]));
+    for (int k = 0; k < pl.n_jit; ++k) jitter += plan_jitter(pl, params, k);
     const MeanEval mean = plan_mean(pl, params);
     const double sig = diag[n] + jitter, alpha = per_step[n], kinv = per_step[N + n];
     const double m = mean(t[n]);

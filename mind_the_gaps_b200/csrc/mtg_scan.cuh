@@ -229,7 +229,7 @@ struct Model {
     {
         plan_coefficients<JR, JC, DUAL>(pl, x, c);
         jit = 0.0;
-        for (int k = 0; k < pl.n_jit; ++k) jit += exp(2.0 * plan_param(pl, x, pl.jit_idx[k]));
+        for (int k = 0; k < pl.n_jit; ++k) jit += plan_jitter(pl, x, k);
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
             bool pair = true;

@@ -39,7 +39,7 @@ __global__ void k_psd_coeffs(const __grid_constant__ Plan pl, const double *__re
     const double *x = params + (size_t)l * pl.n_free;
     PsdCoef c; c.nr = 0; c.nc = 0;
     for (int j = 0; j < pl.jr; ++j) {
-        c.ar[c.nr] = exp(plan_param(pl, x, pl.r_ia[j])); c.cr[c.nr] = exp(plan_param(pl, x, pl.r_ic[j])); ++c.nr;
+        c.ar[c.nr] = plan_real_a(pl, x, j); c.cr[c.nr] = plan_real_c(pl, x, j); ++c.nr;
     }
     for (int j = 0; j < pl.jc; ++j) {
         const double p0 = plan_param(pl, x, pl.c_idx[j][0]), p1 = plan_param(pl, x, pl.c_idx[j][1]);
@@ -48,6 +48,7 @@ __global__ void k_psd_coeffs(const __grid_constant__ Plan pl, const double *__re
         switch (pl.c_kind[j]) {
         case CS_COMPLEX3: a = exp(p0); cc = exp(p1); d = exp(p2); break;
         case CS_COMPLEX4: a = exp(p0); b = exp(p1); cc = exp(p2); d = exp(p3); break;
+        case CS_RAW: a = p0; b = p1; cc = p2; d = p3; break;
         case CS_LORENTZIAN: a = exp(p0); cc = 0.5 * exp(p2) / exp(p1); d = exp(p2); break;
         case CS_COSINUS: a = exp(p0); cc = 0.0; d = exp(p1); break;
         case CS_BENDINGPL: a = exp(p0); b = exp(p1); cc = exp(p2); d = cc; break;

@@ -103,7 +103,10 @@ class GPModelling(object):
             initial_params = self.initial_params
         if optimizer == "auto":
             lib = _native.lib()
-            scan_ok = lib.mtg_device_count() > 0 and bool(lib.mtg_scan_grad_supported(ctypes.byref(self.gp.device_model()), int(self._lightcurve.n)))
+            scan_ok = (not self.gp.needs_host_coefficients()) and lib.mtg_device_count() > 0 and \
+                bool(lib.mtg_scan_grad_supported(ctypes.byref(self.gp.device_model()), int(self._lightcurve.n)))
+            if self.gp.needs_host_coefficients() and int(n_starts) > 1:
+                raise NotImplementedError("multi-start fits run on the device optimiser, which needs built-in kernel terms")
             optimizer = "device" if (scan_ok or int(n_starts) > 1) else "scipy"
         if optimizer not in ("scipy", "device"):
             raise ValueError("optimizer must be 'auto', 'scipy' or 'device'")

@@ -323,3 +323,32 @@ def test_lrt_result_counts_used_simulations():
     assert r.n_used == 3 and r.n_invalid == 1
     p, n = r.pvalue(2.5, return_n=True)
     assert n == 3 and abs(p - (1 - 2 / 3)) < 1e-12
+
+
+def test_user_defined_term_compiles_to_raw_coefficient_model():
+    """A Term subclass without a device map (the way the reference writes its kernels, celerite_models.py:7-34): the host
+    evaluates the coefficients per parameter set; the degenerate (0, 0) real term is dropped."""
+    from mind_the_gaps_b200.celerite import GP, terms
+
+    class MyLorentzian(terms.Term):
+        parameter_names = ("log_S0", "log_Q", "log_omega0")
+
+        def get_real_coefficients(self, params):
+            return 0, 0
+
+        def get_complex_coefficients(self, params):
+            log_S0, log_Q, log_omega0 = params
+            w0 = np.exp(log_omega0)
+            return np.exp(log_S0), 0.0, 0.5 * w0 / np.exp(log_Q), w0
+
+    gp = GP(MyLorentzian(-6.0, 2.0, -12.0) + terms.RealTerm(-5.0, -13.0), mean=0.3)
+    assert gp.needs_host_coefficients() and not gp.device_prior_supported()
+    with pytest.raises(NotImplementedError):
+        gp.device_model()
+    P = np.array([[-6.0, 2.0, -12.0, -5.0, -13.0], [-5.5, 1.0, -11.0, -4.0, -12.0]])
+    m, rows = gp._raw_model_and_rows(P)
+    assert m.n_terms == 3 and list(m.kind[:3]) == [10, 11, 12] and m.n_free == 7
+    w0 = np.exp(P[:, 2])
+    expect = np.column_stack([np.exp(P[:, 3]), np.exp(P[:, 4]), np.exp(P[:, 0]), np.zeros(2), 0.5 * w0 / np.exp(P[:, 1]), w0, np.zeros(2)])
+    np.testing.assert_allclose(rows, expect, rtol=1e-15)
+    np.testing.assert_array_equal(gp.get_parameter_vector(), P[0])          # the GP's own state is restored
