@@ -28,7 +28,7 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
 {
     auto add = [&](int full_idx, double v) { const int pos = pl.src_pos[full_idx]; if (pos >= 0) grad[pos] += v; };
     for (int k = 0; k < pl.n_jit; ++k)
-        add(pl.jit_idx[k], pl.jit_raw[k] ? g.a_sum : g.a_sum * 2.0 * exp(2.0 * plan_param(pl, x, pl.jit_idx[k])));
+        add(pl.jit_idx[k], pl.jit_raw[k] ? g.a_sum : g.a_sum * 2.0 * mtg_exp(2.0 * plan_param(pl, x, pl.jit_idx[k])));
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
         add(pl.r_ia[j], (g.ar[j] + g.a_sum) * (pl.r_raw[j] ? 1.0 : c.ar[j]));
@@ -48,7 +48,7 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
         case CS_BENDINGPL: add(ix[0], ga * a); add(ix[1], gb * b); add(ix[2], (gc + gd) * d); break;
         case CS_MATERN32: add(ix[0], 2.0 * (ga * a + gb * b)); add(ix[1], -(gb * b + gc * cc)); break;
         default: /* CS_SHO */ {
-            const double Q = exp(plan_param(pl, x, ix[1]));
+            const double Q = mtg_exp(plan_param(pl, x, ix[1]));
             if (!DUAL || c.pair[j]) {
                 const double f2 = 4.0 * Q * Q - 1.0, r = 4.0 * Q * Q / f2;
                 add(ix[0], ga * a + gb * b);
@@ -60,7 +60,7 @@ __device__ __forceinline__ void plan_chain(const Plan &pl, const double *__restr
                 const double f = sqrt(1.0 - 4.0 * Q * Q);
                 const double h = 0.5 * (a + a2);                       // = 1/2 S0 w0 Q
                 const double da = h * 4.0 * Q * Q / (f * f * f);
-                const double w0 = exp(plan_param(pl, x, ix[2]));
+                const double w0 = mtg_exp(plan_param(pl, x, ix[2]));
                 const double dcq = 2.0 * w0 * Q / f;
                 add(ix[0], ga * a + ga2 * a2);
                 add(ix[1], ga * (a + da) + ga2 * (a2 - da) + gc * (-cc + dcq) + gc2 * (-c2 - dcq));

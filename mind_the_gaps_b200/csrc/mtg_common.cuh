@@ -63,13 +63,19 @@ __device__ __forceinline__ double plan_param(const Plan &pl, const double *__res
     return pos >= 0 ? x[pos] : pl.full_default[i];
 }
 
+// exp() for the once-per-series parameter maps: ONE out-of-line copy per kernel.  libdevice's exp inlines ~45 instructions
+// per call site and the coefficient maps below have ~25 of them behind a switch: 1.4 k instructions of cold straight-line
+// code that the latency kernels (K9 / K10 / K11, one evaluation = a few thousand instructions per warp) fetched through the
+// instruction cache on every evaluation (ncu: stalled_no_instructions 29 %, profiles/r02a_k11_*).
+static __device__ __noinline__ double mtg_exp(double x) { return exp(x); }
+
 // diagonal jitter of term k, amplitude / rate of real slot j
 __device__ __forceinline__ double plan_jitter(const Plan &pl, const double *__restrict__ x, int k)
-{ const double p = plan_param(pl, x, pl.jit_idx[k]); return pl.jit_raw[k] ? p : exp(2.0 * p); }
+{ const double p = plan_param(pl, x, pl.jit_idx[k]); return pl.jit_raw[k] ? p : mtg_exp(2.0 * p); }
 __device__ __forceinline__ double plan_real_a(const Plan &pl, const double *__restrict__ x, int j)
-{ const double p = plan_param(pl, x, pl.r_ia[j]); return pl.r_raw[j] ? p : exp(p); }
+{ const double p = plan_param(pl, x, pl.r_ia[j]); return pl.r_raw[j] ? p : mtg_exp(p); }
 __device__ __forceinline__ double plan_real_c(const Plan &pl, const double *__restrict__ x, int j)
-{ const double p = plan_param(pl, x, pl.r_ic[j]); return pl.r_raw[j] ? p : exp(p); }
+{ const double p = plan_param(pl, x, pl.r_ic[j]); return pl.r_raw[j] ? p : mtg_exp(p); }
 
 // celerite Model.log_prior: 0 inside the closed box else -inf; the overrides the reference path can reach:
 // BendingPowerlaw (celerite_models.py:85-90) and celerite's ComplexTerm with four parameters.  Returns true when inside.
@@ -77,13 +83,16 @@ __device__ __forceinline__ double plan_real_c(const Plan &pl, const double *__re
 __device__ __forceinline__ bool plan_in_prior(const Plan &pl, const double *__restrict__ x)
 {
     bool ok = true;
+#pragma unroll 1
     for (int k = 0; k < pl.n_free; ++k) {
         const double v = x[k];
         ok = ok && (v >= pl.lo[k]) && (v <= pl.hi[k]);      // NaN -> outside
     }
+#pragma unroll 1
     for (int k = 0; k < pl.n_bpl; ++k)
         ok = ok && !(plan_param(pl, x, pl.bpl_s0[k]) < plan_param(pl, x, pl.bpl_q[k]));
     // celerite ComplexTerm.log_prior with a fitted log_b: -inf when a c < b d (the term is then not positive definite)
+#pragma unroll 1
     for (int j = 0; j < pl.jc; ++j)
         if (pl.c_kind[j] == CS_COMPLEX4) {
             const int *ix = pl.c_idx[j];
@@ -117,25 +126,31 @@ __device__ __forceinline__ void plan_coefficients(const Plan &pl, const double *
     }
 #pragma unroll
     for (int j = 0; j < JC; ++j) {
-        const double p0 = plan_param(pl, x, pl.c_idx[j][0]);
-        const double p1 = plan_param(pl, x, pl.c_idx[j][1]);
+        const int kind = pl.c_kind[j];
+        const double p0 = plan_param(pl, x, pl.c_idx[j][0]), p1 = plan_param(pl, x, pl.c_idx[j][1]);
+        const double p2 = plan_param(pl, x, pl.c_idx[j][2]), p3 = plan_param(pl, x, pl.c_idx[j][3]);
+        // the exponentials every kind needs, through the single out-of-line exp (Matern-3/2 takes e^{2 log_sigma}, e^{-log_rho})
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+        if (kind != CS_RAW) {
+            e0 = mtg_exp(kind == CS_MATERN32 ? 2.0 * p0 : p0);
+            e1 = mtg_exp(kind == CS_MATERN32 ? -p1 : p1);
+            if (kind != CS_COSINUS && kind != CS_MATERN32) e2 = mtg_exp(p2);
+            if (kind == CS_COMPLEX4) e3 = mtg_exp(p3);
+        }
         double a, b = 0.0, cc, d;
         bool pair = true; double a2 = 0.0, c2 = 0.0;
-        switch (pl.c_kind[j]) {
-        case CS_COMPLEX3: a = exp(p0); cc = exp(p1); d = exp(plan_param(pl, x, pl.c_idx[j][2])); break;
-        case CS_COMPLEX4: a = exp(p0); b = exp(p1); cc = exp(plan_param(pl, x, pl.c_idx[j][2]));
-                          d = exp(plan_param(pl, x, pl.c_idx[j][3])); break;
-        case CS_RAW:      a = p0; b = p1; cc = plan_param(pl, x, pl.c_idx[j][2]); d = plan_param(pl, x, pl.c_idx[j][3]); break;
-        case CS_LORENTZIAN: { const double w0 = exp(plan_param(pl, x, pl.c_idx[j][2]));
-                          a = exp(p0); cc = 0.5 * w0 / exp(p1); d = w0; } break;
-        case CS_COSINUS:  a = exp(p0); cc = 0.0; d = exp(p1); break;
-        case CS_BENDINGPL: { const double w0 = exp(plan_param(pl, x, pl.c_idx[j][2]));
-                          a = exp(p0); b = exp(p1); cc = w0; d = w0; } break;
+        switch (kind) {
+        case CS_COMPLEX3: a = e0; cc = e1; d = e2; break;
+        case CS_COMPLEX4: a = e0; b = e1; cc = e2; d = e3; break;
+        case CS_RAW:      a = p0; b = p1; cc = p2; d = p3; break;
+        case CS_LORENTZIAN: a = e0; cc = 0.5 * e2 / e1; d = e2; break;
+        case CS_COSINUS:  a = e0; cc = 0.0; d = e1; break;
+        case CS_BENDINGPL: a = e0; b = e1; cc = e2; d = e2; break;
         case CS_MATERN32: { const double eps = pl.c_extra[j];
-                          const double w0 = sqrt(3.0) * exp(-p1); const double S0 = exp(2.0 * p0) / w0;
+                          const double w0 = sqrt(3.0) * e1; const double S0 = e0 / w0;
                           a = w0 * S0; b = w0 * w0 * S0 / eps; cc = w0; d = eps; } break;
         default: /* CS_SHO */ {
-                          const double S0 = exp(p0), Q = exp(p1), w0 = exp(plan_param(pl, x, pl.c_idx[j][2]));
+                          const double S0 = e0, Q = e1, w0 = e2;
                           if (!DUAL || Q >= 0.5) {
                               const double f = sqrt(4.0 * Q * Q - 1.0);
                               a = S0 * w0 * Q; b = a / f; cc = 0.5 * w0 / Q; d = cc * f;

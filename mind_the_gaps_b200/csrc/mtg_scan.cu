@@ -49,13 +49,13 @@ k9_loglike_scan(const __grid_constant__ Plan pl, const BatchArgs a, int staged)
     const int ds = b / a.group;
     const bool dsm = (a.flags & MTG_FLAG_DS_MEAN) != 0;
     int st;
-    double ll;
+    const double *st_t = a.t, *st_y = a.y + ds, *st_d = a.diag + ds;
+    size_t stride = (size_t)a.S;
     if (staged) {
         stage_series(k9_series_sm, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S);
-        ll = series_loglike<JR, JC, DUAL, true>(pl, x, a.N, k9_series_sm, k9_series_sm + a.N, k9_series_sm + 2 * a.N, 1, dsm,
-                                                dsm ? a.ds_mean[ds] : 0.0, sc, &st);
-    } else
-        ll = series_loglike<JR, JC, DUAL, false>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsm ? a.ds_mean[ds] : 0.0, sc, &st);
+        st_t = k9_series_sm; st_y = k9_series_sm + a.N; st_d = k9_series_sm + 2 * a.N; stride = 1;
+    }
+    double ll = series_loglike<JR, JC, DUAL, false>(pl, x, a.N, st_t, st_y, st_d, stride, dsm, dsm ? a.ds_mean[ds] : 0.0, sc, &st);
     if (threadIdx.x == 0) {
         if (!inside) { ll = -INFINITY; st = 3; }
         a.out_ll[b] = ll;
@@ -159,13 +159,16 @@ k10_ensemble_scan(const __grid_constant__ Plan pl, const EnsembleArgs a, unsigne
     const bool track_best = a.best_lp != nullptr;
     double my_best = -INFINITY;                        // thread 0: best log-probability this CTA has seen
 
-    if (staged) stage_series(k10_series_sm, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S);
+    const double *st_t = a.t, *st_y = a.y + ds, *st_d = a.diag + ds;
+    size_t stride = (size_t)a.S;
+    if (staged) {
+        stage_series(k10_series_sm, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S);
+        st_t = k10_series_sm; st_y = k10_series_sm + a.N; st_d = k10_series_sm + 2 * a.N; stride = 1;
+    }
     auto log_prob = [&](const double *x) -> double {   // CTA-collective; x in shared memory
         if (!plan_in_prior(pl, x)) return -INFINITY;   // uniform over the CTA
         int st;
-        if (staged)
-            return series_loglike<JR, JC, DUAL, true>(pl, x, a.N, k10_series_sm, k10_series_sm + a.N, k10_series_sm + 2 * a.N, 1, dsm, dsv, sc, &st);
-        return series_loglike<JR, JC, DUAL, false>(pl, x, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S, dsm, dsv, sc, &st);
+        return series_loglike_call<JR, JC, DUAL>(pl, x, a.N, st_t, st_y, st_d, stride, dsm, dsv, sc, &st);
     };
 
     // ---- initial log-probabilities: this CTA owns walkers slot and slot + H at the start ----------------
