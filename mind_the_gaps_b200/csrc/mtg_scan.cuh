@@ -421,81 +421,9 @@ struct Scratch {
     double result; int status;
 };
 
-// Phase 2 of the scan: from every thread's composite element e, the FILTERED state (mean mu, covariance P) just before the
-// thread's first observation (thread 0: the prior 0, P_inf).  CTA-collective.  The three places the operator is applied --
-// the 5 shuffle levels inside a warp, the 3 levels over the warp totals (warp 0, through shared memory) and the final
-// "warps before, then lanes before" step -- are iterations of ONE loop, so `combine` (some 700 instructions for J = 3) is
-// inlined once: the scan kernels were fetching 130 KB of straight-line code per evaluation and stalling on the
-// instruction cache (ncu: stalled_no_instructions 29 % in K11, profiles/r02a_k11_*).
-template <int JR, int JC, bool DUAL>
-__device__ __forceinline__ void scan_exclusive(const Model<JR, JC, DUAL> &m, const Elem<JR + 2 * JC> &e, Scratch<JR + 2 * JC> &sc,
-                                               double *mu, double *P)
-{
-    constexpr int J = JR + 2 * JC;
-    constexpr int NE = sizeof(Elem<J>) / sizeof(double);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    Elem<J> X = e, keep;
-    keep.identity();
-#pragma unroll 1
-    for (int step = 0; step < 9; ++step) {
-        Elem<J> prev;
-        bool active;
-        if (step < 5) {                                   // inclusive scan inside the warp
-            const int d = 1 << step;
-            prev = shfl_up<J>(X, d, 32);
-            active = lane >= d;
-        } else if (step < 8) {                            // the 8 warp totals, scanned by warp 0
-            if (step == 5) {
-                keep = X;                                 // this thread's inclusive prefix within its warp
-                __syncthreads();                          // scratch free (a previous evaluation may still be reading it)
-                if (lane == 31) {
-                    const double *src = reinterpret_cast<const double *>(&X);
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) sc.warp_tot[wid][i] = src[i];
-                }
-                __syncthreads();
-                X.identity();
-                if (wid == 0 && lane < K9_WARPS) {
-                    double *dst = reinterpret_cast<double *>(&X);
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) dst[i] = sc.warp_tot[lane][i];
-                }
-            }
-            const int d = 1 << (step - 5);
-            prev = shfl_up<J>(X, d, 32);
-            active = wid == 0 && lane >= d && lane < K9_WARPS;
-        } else {                                          // exclusive prefix: (warps before) then (lanes before)
-            if (wid == 0 && lane < K9_WARPS) {
-                const double *src = reinterpret_cast<const double *>(&X);
-#pragma unroll
-                for (int i = 0; i < NE; ++i) sc.warp_tot[lane][i] = src[i];
-            }
-            __syncthreads();
-            X = shfl_up<J>(keep, 1, 32);
-            if (lane == 0) X.identity();
-            prev.identity();
-            active = wid > 0;
-            if (active) {
-                double *dst = reinterpret_cast<double *>(&prev);
-#pragma unroll
-                for (int i = 0; i < NE; ++i) dst[i] = sc.warp_tot[wid - 1][i];
-            }
-        }
-        if (active) { Elem<J> r = X; combine<J>(prev, X, r, step < 8); X = r; }
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < J; ++i) mu[i] = 0.0;
-        m.stationary(P);
-    } else {
-#pragma unroll
-        for (int i = 0; i < J; ++i) mu[i] = X.b[i];
-#pragma unroll
-        for (int i = 0; i < Elem<J>::NS; ++i) P[i] = X.C[i];
-    }
-}
-
-// Phases 1 and 2 of the scan: composite element of this thread's observations, then scan_exclusive.
+// Phases 1 and 2 of the scan: composite element of this thread's observations, inclusive scan over the CTA, and from it the
+// FILTERED state (mean mu, covariance P) just before the thread's first observation (thread 0: the prior 0, P_inf).
+// CTA-collective: every thread calls it.
 template <int JR, int JC, bool DUAL, bool STAGED>
 __device__ __forceinline__ void scan_prefix(const Model<JR, JC, DUAL> &m, const MeanEval &mean, int N, const double *__restrict__ t,
                                             const double *__restrict__ yp, const double *__restrict__ dp, size_t S,
@@ -505,9 +433,12 @@ __device__ __forceinline__ void scan_prefix(const Model<JR, JC, DUAL> &m, const 
     auto Y_ = [&](int n) { return STAGED ? yp[n] : yp[(size_t)n * S]; };
     auto D_ = [&](int n) { return STAGED ? dp[n] : dp[(size_t)n * S]; };
     constexpr int J = JR + 2 * JC;
-    const int tid = threadIdx.x;
+    constexpr int NE = sizeof(Elem<J>) / sizeof(double);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int CH = (N + K9_THREADS - 1) / K9_THREADS;
     const int n0 = min(tid * CH, N), n1 = min(n0 + CH, N);
+
+    // ---- phase 1: composite of this thread's observations -------------------------------------------
     Elem<J> e;
     e.identity();
     if (tid == 0) {                               // the prior: mean 0, covariance P_inf
@@ -520,7 +451,66 @@ __device__ __forceinline__ void scan_prefix(const Model<JR, JC, DUAL> &m, const 
         const double dt = n > 0 ? tn - T_(n - 1) : 0.0;
         append<JR, JC, DUAL>(m, e, dt, Y_(n) - mean(tn), D_(n) + m.jit);
     }
-    scan_exclusive<JR, JC, DUAL>(m, e, sc, mu, P);
+
+    // ---- phase 2: inclusive scan over the CTA ---------------------------------------------------------
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const Elem<J> prev = shfl_up<J>(e, d, 32);
+        if (lane >= d) { Elem<J> r; combine<J>(prev, e, r, true); e = r; }
+    }
+    __syncthreads();                              // scratch free (a previous evaluation may still be reading it)
+    if (lane == 31) {
+        const double *src = reinterpret_cast<const double *>(&e);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) sc.warp_tot[wid][i] = src[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        Elem<J> w;
+        w.identity();
+        if (lane < K9_WARPS) {
+            double *dst = reinterpret_cast<double *>(&w);
+#pragma unroll
+            for (int i = 0; i < NE; ++i) dst[i] = sc.warp_tot[lane][i];
+        }
+#pragma unroll 1
+        for (int d = 1; d < K9_WARPS; d <<= 1) {
+            const Elem<J> prev = shfl_up<J>(w, d, 32);
+            if (lane >= d && lane < K9_WARPS) { Elem<J> r; combine<J>(prev, w, r, true); w = r; }
+        }
+        if (lane < K9_WARPS) {
+            const double *src = reinterpret_cast<const double *>(&w);
+#pragma unroll
+            for (int i = 0; i < NE; ++i) sc.warp_tot[lane][i] = src[i];
+        }
+    }
+    __syncthreads();
+    // exclusive prefix of this thread: (warps before) then (lanes before)
+    Elem<J> ex = shfl_up<J>(e, 1, 32);
+    if (lane == 0) ex.identity();
+    if (wid > 0) {
+        Elem<J> wp;
+        double *dst = reinterpret_cast<double *>(&wp);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) dst[i] = sc.warp_tot[wid - 1][i];
+        Elem<J> r;
+        combine<J>(wp, ex, r, false);
+#pragma unroll
+        for (int i = 0; i < J; ++i) ex.b[i] = r.b[i];
+#pragma unroll
+        for (int i = 0; i < Elem<J>::NS; ++i) ex.C[i] = r.C[i];
+    }
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < J; ++i) mu[i] = 0.0;
+        m.stationary(P);
+    } else {
+#pragma unroll
+        for (int i = 0; i < J; ++i) mu[i] = ex.b[i];
+#pragma unroll
+        for (int i = 0; i < Elem<J>::NS; ++i) P[i] = ex.C[i];
+    }
 }
 
 // log-likelihood of ONE series by the whole CTA (every thread calls it; every thread gets the result).

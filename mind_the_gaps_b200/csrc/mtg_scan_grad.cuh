@@ -189,47 +189,25 @@ __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const doub
     MeanEval mean = plan_mean(pl, x);
     if (ds_mean) { mean.kind = MTG_MEAN_CONSTANT; mean.p0 = ds_mean_value; }
 
-    // ---- forward: two passes over the thread's chunk through ONE copy of the code -- pass 0 builds the composite element
-    //      for the scan (from a point mass; thread 0 from the prior), pass 1 starts from the scan's chunk-start state,
-    //      tapes (m, P) before every step, accumulates the likelihood and leaves (Phi, q, Omega) in (e.A, e.eta, e.Jm) ----
+    // ---- forward: chunk-start state from the scan, then the chunk itself ----------------------------------------
     Elem<J> e;
+    e.identity();
+    scan_prefix<JR, JC, DUAL, true>(m, mean, N, t, yp, dp, 1, sc, e.b, e.C);
     double chi2 = 0.0, prod = 1.0; int esum = 0; bool bad = false;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 0) {
-            e.identity();
-            if (tid == 0) {                           // the prior: mean 0, covariance P_inf
+    for (int n = n0; n < n1; ++n) {
+        const int i = n - n0;
 #pragma unroll
-                for (int i = 0; i < J * J; ++i) e.A[i] = 0.0;
-                m.stationary(e.C);
-            }
-        } else {
-            double mu[J], P[NS];
-            scan_exclusive<JR, JC, DUAL>(m, e, sc, mu, P);
-            e.identity();
+        for (int k = 0; k < J; ++k) slot(i, k) = e.b[k];
 #pragma unroll
-            for (int i = 0; i < J; ++i) e.b[i] = mu[i];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) e.C[i] = P[i];
-        }
-        chi2 = 0.0; prod = 1.0; esum = 0; bad = false;
-        for (int n = n0; n < n1; ++n) {
-            if (pass == 1) {
-                const int i = n - n0;
-#pragma unroll
-                for (int k = 0; k < J; ++k) slot(i, k) = e.b[k];
-#pragma unroll
-                for (int k = 0; k < NS; ++k) slot(i, J + k) = e.C[k];
-            }
-            const double tn = t[n];
-            const double dt = n > 0 ? tn - t[n - 1] : 0.0;
-            double s, v;
-            append_sv<JR, JC, DUAL>(m, e, dt, yp[n] - mean(tn), dp[n] + m.jit, &s, &v);
-            bad = bad || !(s > 0.0);
-            chi2 = fma(v * v, 1.0 / s, chi2);
-            prod *= s;
-            { int ex2; prod = frexp(prod, &ex2); esum += ex2; }
-        }
+        for (int k = 0; k < NS; ++k) slot(i, J + k) = e.C[k];
+        const double tn = t[n];
+        const double dt = n > 0 ? tn - t[n - 1] : 0.0;
+        double s, v;
+        append_sv<JR, JC, DUAL>(m, e, dt, yp[n] - mean(tn), dp[n] + m.jit, &s, &v);
+        bad = bad || !(s > 0.0);
+        chi2 = fma(v * v, 1.0 / s, chi2);
+        prod *= s;
+        { int ex2; prod = frexp(prod, &ex2); esum += ex2; }
     }
     double part = chi2 + log(prod) + (double)esum * MTG_LN2;
     int badi = bad ? 1 : 0;
@@ -258,64 +236,59 @@ __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const doub
         return ll;
     }
 
-    // ---- suffix scan of the chunk elements (Phi, q, Omega): intra-warp levels, the 8 warp totals (warp 0), and the final
-    //      "lanes after, then warps after" step as iterations of one loop (one inlined copy of `compose`) -----------------
-    BElem<J> ex;
+    // ---- suffix scan of the chunk elements (Phi, q, Omega) -------------------------------------------------------
+    BElem<J> be;
 #pragma unroll
-    for (int i = 0; i < J * J; ++i) ex.A[i] = e.A[i];
+    for (int i = 0; i < J * J; ++i) be.A[i] = e.A[i];
 #pragma unroll
-    for (int i = 0; i < J; ++i) ex.q[i] = e.eta[i];
+    for (int i = 0; i < J; ++i) be.q[i] = e.eta[i];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) ex.Om[i] = e.Jm[i];
-    {
-        BElem<J> keep;
-        keep.identity();
+    for (int i = 0; i < NS; ++i) be.Om[i] = e.Jm[i];
 #pragma unroll 1
-        for (int step = 0; step < 9; ++step) {
-            BElem<J> nx;
-            bool active;
-            if (step < 5) {
-                const int d = 1 << step;
-                nx = shfl_down<J>(ex, d);
-                active = lane + d < 32;
-            } else if (step < 8) {
-                if (step == 5) {
-                    keep = ex;                            // inclusive suffix within the warp
-                    if (lane == 0) {
-                        const double *src = reinterpret_cast<const double *>(&ex);
+    for (int d = 1; d < 32; d <<= 1) {
+        const BElem<J> nx = shfl_down<J>(be, d);
+        if (lane + d < 32) { BElem<J> r; compose<J>(be, nx, r, true); be = r; }
+    }
+    if (lane == 0) {
+        const double *src = reinterpret_cast<const double *>(&be);
 #pragma unroll
-                        for (int i = 0; i < NB; ++i) gs.warp_tot[wid][i] = src[i];
-                    }
-                    __syncthreads();
-                    ex.identity();
-                    if (wid == 0 && lane < K9_WARPS) {
-                        double *dst = reinterpret_cast<double *>(&ex);
+        for (int i = 0; i < NB; ++i) gs.warp_tot[wid][i] = src[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        BElem<J> w;
+        w.identity();
+        if (lane < K9_WARPS) {
+            double *dst = reinterpret_cast<double *>(&w);
 #pragma unroll
-                        for (int i = 0; i < NB; ++i) dst[i] = gs.warp_tot[lane][i];
-                    }
-                }
-                const int d = 1 << (step - 5);
-                nx = shfl_down<J>(ex, d);
-                active = wid == 0 && lane + d < K9_WARPS;
-            } else {
-                if (wid == 0 && lane < K9_WARPS) {
-                    const double *src = reinterpret_cast<const double *>(&ex);
-#pragma unroll
-                    for (int i = 0; i < NB; ++i) gs.warp_tot[lane][i] = src[i];
-                }
-                __syncthreads();
-                ex = shfl_down<J>(keep, 1);
-                if (lane == 31) ex.identity();
-                nx.identity();
-                active = wid < K9_WARPS - 1;
-                if (active) {
-                    double *dst = reinterpret_cast<double *>(&nx);
-#pragma unroll
-                    for (int i = 0; i < NB; ++i) dst[i] = gs.warp_tot[wid + 1][i];
-                }
-            }
-            if (active) { BElem<J> r = ex; compose<J>(ex, nx, r, step < 8); ex = r; }
+            for (int i = 0; i < NB; ++i) dst[i] = gs.warp_tot[lane][i];
         }
+#pragma unroll 1
+        for (int d = 1; d < K9_WARPS; d <<= 1) {
+            const BElem<J> nx = shfl_down<J>(w, d);
+            if (lane + d < K9_WARPS) { BElem<J> r; compose<J>(w, nx, r, true); w = r; }
+        }
+        if (lane < K9_WARPS) {
+            const double *src = reinterpret_cast<const double *>(&w);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) gs.warp_tot[lane][i] = src[i];
+        }
+    }
+    __syncthreads();
+    // exclusive suffix of this thread: (lanes after it in the warp) then (warps after it)
+    BElem<J> ex = shfl_down<J>(be, 1);
+    if (lane == 31) ex.identity();
+    if (wid < K9_WARPS - 1) {
+        BElem<J> wp;
+        double *dst = reinterpret_cast<double *>(&wp);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) dst[i] = gs.warp_tot[wid + 1][i];
+        BElem<J> r;
+        compose<J>(ex, wp, r, false);
+#pragma unroll
+        for (int i = 0; i < J; ++i) ex.q[i] = r.q[i];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) ex.Om[i] = r.Om[i];
     }
 
     // ---- reverse: adjoint sweep over this thread's chunk ------------------------------------------------------------
