@@ -296,9 +296,13 @@ class GPModelling(object):
         return counts
 
     # -- simulation from the posteriors -------------------------------------------------------------------------
-    def generate_from_posteriors(self, nsims=10, cpus=8, pdf="Gaussian", extension_factor=2, sigma_noise=None):
+    def generate_from_posteriors(self, nsims=10, cpus=8, pdf="Gaussian", extension_factor=2, sigma_noise=None, fft_length="fast"):
         """``nsims`` lightcurves, each simulated from one random posterior sample of the kernel parameters
-        with the observing window, exposures and noise model of the data (gpmodelling.py:478-539)."""
+        with the observing window, exposures and noise model of the data (gpmodelling.py:478-539).
+
+        ``fft_length``: only the binned lightcurves leave this call, so the internal regular grid is lengthened (by < 0.5 %) to
+        the next 7-smooth length by default -- the same process, statistically (tests/test_simulator_stats_gpu.py), without
+        the Bluestein FFT a real window's grid length usually needs; ``"exact"`` keeps the reference's own grid length."""
         if self._mcmc_samples is None:
             raise RuntimeError("Posteriors have not been derived. Please run derive_posteriors prior to calling this method.")
         if nsims >= len(self._mcmc_samples):
@@ -306,7 +310,7 @@ class GPModelling(object):
                           "so many samples will be drawn more than once" % (nsims, len(self._mcmc_samples)))
         param_samples = self._mcmc_samples[np.random.randint(len(self._mcmc_samples), size=nsims)]
         simulator = self._lightcurve.get_simulator(self.gp.kernel.get_psd, pdf, sigma_noise=sigma_noise,
-                                                   extension_factor=extension_factor)
+                                                   extension_factor=extension_factor, fft_length=fft_length)
         nk = self.gp.kernel.vector_size
         rates = simulator.generate_lightcurves(nsims, parameters=param_samples[:, :nk])
         noisy, dy = simulator.add_noise(rates)

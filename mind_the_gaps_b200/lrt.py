@@ -188,6 +188,10 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     batched L-BFGS (a latency-bound tail of ~1 ms rounds) then overlap the FFTs and the bulk of the other chunks'
     fits instead of idling the GPU.
 
+    ``simulator_kwargs``: passed to ``Simulator``; by default the regular grid is lengthened to the next 7-smooth length
+    (``fft_length="fast"``: only binned lightcurves are used here, and the simulated process is statistically the same),
+    ``{"fft_length": "exact"}`` keeps the reference's own grid length (usually a Bluestein FFT, ~2x slower simulation).
+
     ``refine_walkers, refine_steps``: when both are positive every fit is followed, as in the reference's notebook
     (``GPModelling(lc, kernel).derive_posteriors(fit=True, walkers=30, max_steps=500)`` then ``max_loglikelihood``,
     tutorial_ppp.ipynb cells 11-13), by a short stretch-move chain started in a 10 % Gaussian ball around the optimum
@@ -281,7 +285,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         stream.wait_stream(main_stream)
         sp = stream.cuda_stream
         sim = lightcurve.get_simulator(null_kernel.get_psd, pdf, sigma_noise=sigma_noise, extension_factor=extension_factor,
-                                       **(simulator_kwargs or {}))
+                                       **dict({"fft_length": "fast"}, **(simulator_kwargs or {})))
         h = sim._sim()
         local = {"simulate_ms": 0.0, "fit_null_ms": 0.0, "fit_alt_ms": 0.0, "n_invalid": 0}
         try:

@@ -232,3 +232,31 @@ def test_segment_duration_and_sampling():        # simulator_test.py:255-304: cu
         simu = Simulator(powerlaw(1.0), timestamps, dt, 0.5, extension_factor=50, aliasing_factor=1)
         lc = simu.simulate_regularly_sampled()
         assert cut_random_segment(lc, timestamps[-1] - timestamps[0]).dt == dt
+
+
+def test_fast_grid_is_statistically_the_reference_grid():
+    """``fft_length="fast"`` (the default of the LRT driver and of generate_from_posteriors, where only binned lightcurves
+    leave the call) lengthens the regular grid by < 0.5 % to a 7-smooth length.  On a gapped window the binned lightcurves
+    of both grids must be the same process: per-lightcurve mean, variance and lag-1 autocovariance follow the same
+    distributions (two-sample KS), and the ensemble variances agree."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import window
+    from mind_the_gaps_b200.lightcurves import GappyLightcurve
+    day = 86400.0
+    t, exposures = window(300, 7)
+    lc = GappyLightcurve(t, np.full(300, 0.5), np.full(300, 0.02), exposures)
+    var = (0.1 * 0.5) ** 2
+    psd = BendingPowerlaw(S0=var, omega0=2 * np.pi / (20 * day))
+    L = 3000
+    out = {}
+    for mode in ("exact", "fast"):
+        sim = lc.get_simulator(psd, "Gaussian", extension_factor=2, fft_length=mode)
+        out[mode] = sim.generate_lightcurves(L, seed=11 if mode == "exact" else 12)
+        out[mode + "_n"] = sim.fftndatapoints
+        sim.close()
+    assert out["exact_n"] < out["fast_n"] <= 1.005 * out["exact_n"]
+    for f in (lambda r: r.mean(axis=1), lambda r: r.var(axis=1), lambda r: np.mean((r[:, 1:] - 0.5) * (r[:, :-1] - 0.5), axis=1)):
+        assert sps.ks_2samp(f(out["exact"]), f(out["fast"])).pvalue > 1e-3
+    v = {mode: np.mean((out[mode] - 0.5) ** 2) for mode in ("exact", "fast")}      # ensemble variance about the true mean
+    assert abs(v["fast"] / v["exact"] - 1.0) < 0.05, v
