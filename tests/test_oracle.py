@@ -187,3 +187,33 @@ def test_oracle_sampler_draw_order_and_posterior():
     one = osamp.stretch_move_run(lambda x: np.zeros(len(x)), np.array([[0.0], [4.0]]), 1, np.array([[0, 1]]),
                                  np.zeros((1, 2, 1)), np.zeros((1, 2, 1), dtype=int), np.zeros((1, 2, 1)))[0]
     np.testing.assert_array_equal(one[0], [[2.0], [3.0]])
+
+
+# ---- oracle.kalman.grad_chunked_adjoint: the NumPy statement of kernel K11 --------------------------------------------------
+@pytest.mark.parametrize("threads", [1, 3, 8, 64, 300])
+def test_chunked_adjoint_equals_complex_step_for_any_chunking(threads):
+    """Reverse mode through the Kalman filter chunk by chunk -- per-chunk (Phi, q, Omega), suffix composition, independent
+    chunk adjoint sweeps (what K11 runs with one chunk per thread) -- gives the gradient of the celerite log-likelihood with
+    respect to every coefficient, the jitter and the residuals: equal to complex-step differentiation of the oracle's
+    recursion, whatever the number of chunks (more chunks than observations included)."""
+    from oracle import kalman
+    t, y, dy, _ = fake_lightcurve(157, 3)
+    resid = y - y.mean(); diag = (dy + 1e-12) ** 2
+    ar = np.array([0.003, 0.001]); cr = np.array([2e-6, 3e-7])
+    ac = np.array([0.002, 0.0015]); bc = np.array([0.0, 0.0004]); cc = np.array([1e-7, 4e-7]); dc = np.array([7e-6, 2e-6]); jit = 1e-4
+    ll, g = kalman.grad_chunked_adjoint(t, resid, diag, ar, cr, ac, bc, cc, dc, jitter=jit, threads=threads)
+    co = dict(ar=ar, cr=cr, ac=ac, bc=bc, cc=cc, dc=dc)
+    ref = gp.loglike_recursion(t, resid, diag, *[co[k][None] for k in ("ar", "cr", "ac", "bc", "cc", "dc")], jitter=jit)[0]
+    assert abs(ll - ref) < 1e-12 * abs(ref)
+    h = 1e-30
+    for name in co:
+        for j in range(2):
+            c = {k: v.astype(complex)[None] for k, v in co.items()}
+            c[name][0, j] += 1j * h
+            d = np.imag(gp.loglike_recursion(t, resid, diag, c["ar"], c["cr"], c["ac"], c["bc"], c["cc"], c["dc"], jitter=jit)[0]) / h
+            assert abs(g[name][j] - d) <= 1e-11 * max(abs(d), 1.0), (name, j, g[name][j], d)
+    d = np.imag(gp.loglike_recursion(t, resid, diag, *[co[k][None] for k in ("ar", "cr", "ac", "bc", "cc", "dc")], jitter=jit + 1j * h)[0]) / h
+    assert abs(g["jitter"] - d) <= 1e-11 * abs(d)
+    rc = resid.astype(complex); rc[40] += 1j * h
+    d = np.imag(gp.loglike_recursion(t, rc, diag, *[co[k][None] for k in ("ar", "cr", "ac", "bc", "cc", "dc")], jitter=jit)[0]) / h
+    assert abs(g["resid"][40] - d) <= 1e-11 * abs(d)

@@ -22,3 +22,9 @@ for kern in ("scan", "k8"):
     s = DeviceEnsembleSampler(12, gp, y, seed=3, block=6, kernel=kern)
     s.run_mcmc(p, 6)
     print(kern, "chain checksum %.12f" % float(np.sum(s.get_chain())))
+# round 2: the parallel-in-time gradient K11, K2 beside it, and the persistent L-BFGS kernel (a small multi-start fit)
+_, g11 = gp.grad_log_likelihood_batch(y, p, kernel="scan"); _, g2 = gp.grad_log_likelihood_batch(y, p, kernel="k2")
+print("K11 vs K2 gradient max rel diff %.1e" % (np.max(np.abs(g11 - g2)) / np.max(np.abs(g2))))
+from mind_the_gaps_b200 import fitting
+res = fitting.fit_lightcurves(gp, t, np.stack([y, y[::-1]]), np.stack([dy, dy]), x0=p0, n_starts=3, rng=np.random.default_rng(0), max_iter=8)
+print("persistent L-BFGS: fun", [round(r.fun, 6) for r in res], "nit", [int(r.nit) for r in res])
