@@ -528,6 +528,10 @@ def secondary_measurements(torch, lib, _native, model, gp, dev, stream, d_t, d_y
     # ---- config C5: N = 1e5 points, 3 x SHOTerm + RealTerm (J = 7), 1e5 parameter sets over the ranks, shared data
     try:
         out["c5_long_baseline_sweep"] = c5_measurement(torch, lib, _native, dev, stream, timed, rank, world)
+        # the same sweep at a batch that fills whole waves of the J = 7 kernel (148 SMs x 2 CTAs x 128 threads x 3): the
+        # config's 1e5 sets are 2.64 waves and pay for 3
+        full = c5_measurement(torch, lib, _native, dev, stream, timed, rank, 1, n_sets=148 * 256 * 3)
+        out["c5_long_baseline_sweep"]["full_waves"] = {k: full[k] for k in ("parameter_sets_per_gpu", "ms", "evals_per_s_per_gpu", "tflops_algorithmic_per_gpu")}
     except Exception as exc:
         out["c5_long_baseline_sweep"] = {"error": repr(exc)}
     # ---- config C3: simulator ensemble (TK95 Gaussian + Poisson; E13 lognormal + Kraft on a bounded sample)
@@ -732,6 +736,8 @@ def main():
             c5_tf = dig(extras, "c5_long_baseline_sweep", "tflops_algorithmic_per_gpu")
             line["c5_frac"] = (c5_tf / pk_value) if (c5_tf and pk_value) else None
             line["c5_evals_per_s"] = (dig(extras, "c5_long_baseline_sweep", "evals_per_s_per_gpu") or 0) * world or None
+            c5_tf_full = dig(extras, "c5_long_baseline_sweep", "full_waves", "tflops_algorithmic_per_gpu")
+            line["c5_frac_full_waves"] = (c5_tf_full / pk_value) if (c5_tf_full and pk_value) else None
             line["grad_scan_us_148_series"] = dig(extras, "loglike_grad_scan", "us_148_series")
             line["fit_one_lightcurve_ms"] = dig(extras, "gpmodelling_public_api_one_lightcurve", "null_DRW", "fit_ms")
         if not args.no_cpu_baseline and world == 1:

@@ -27,8 +27,12 @@
 #define K1_NARROW_THREADS 256
 #define K1_NARROW_BLOCKS 2
 #endif
-constexpr int k1_threads(int J) { return J <= K1_NARROW_J ? K1_NARROW_THREADS : 128; }
-constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? K1_NARROW_BLOCKS : 1; }
+#ifndef K1_WIDE_THREADS
+#define K1_WIDE_THREADS 128
+#define K1_WIDE_BLOCKS 1
+#endif
+constexpr int k1_threads(int J) { return J <= K1_NARROW_J ? K1_NARROW_THREADS : K1_WIDE_THREADS; }
+constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? K1_NARROW_BLOCKS : K1_WIDE_BLOCKS; }
 #ifndef K1_UNROLL
 #define K1_UNROLL 2
 #endif
