@@ -225,7 +225,6 @@ int    mtg_k9_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);
 bool   mtg_k9_supports(const Plan &pl);
 int    mtg_k11_dispatch(const Plan &pl, const BatchArgs &a, cudaStream_t stream);     // scan gradient (mtg_scan_grad.cu); honours a.index / a.count
 bool   mtg_k11_supports(const Plan &pl, int N);
-size_t mtg_k11_smem_bytes(const Plan &pl, int N);
 long long mtg_scan_grad_max_batch();
 size_t mtg_k2_tape_bytes_per_series(const Plan &pl, int N);
 int    mtg_k2_chunk(const Plan &pl, int N, int B);

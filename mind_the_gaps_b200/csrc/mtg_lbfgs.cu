@@ -275,15 +275,17 @@ struct LbfgsLocal {
 template <int JR, int JC, bool DUAL>
 __global__ void __launch_bounds__(K9_THREADS, 1)
 k_lbfgs_persist(const __grid_constant__ Plan pl, const BatchArgs a, const LbfgsState s, const __grid_constant__ LbfgsParams p,
-                const int32_t *__restrict__ list, const int32_t *__restrict__ count, int32_t *cursor, long long max_rounds)
+                const int32_t *__restrict__ list, const int32_t *__restrict__ count, int32_t *cursor, long long max_rounds,
+                const K11Layout lay, double *__restrict__ scratch)
 {
     constexpr int J = JR + 2 * JC;
     __shared__ k9::Scratch<J> sc;
     __shared__ k9::GScratch<JR, JC, DUAL> gs;
     __shared__ LbfgsLocal loc;
     __shared__ int cur, done_flag;
-    extern __shared__ double lb_dyn[];               // [3][N] series, then K11's tape
-    double *series = lb_dyn, *tape = lb_dyn + 3 * (size_t)a.N;
+    extern __shared__ double lb_dyn[];               // [3][N] series when staged, then K11's tape when it fits (mtg_k11_layout)
+    double *series = lb_dyn;
+    double *tape = lay.tape_smem ? lb_dyn + (lay.stage ? 3 * (size_t)a.N : 0) : scratch + (size_t)blockIdx.x * lay.scratch_doubles;
     const int tid = threadIdx.x, T = blockDim.x, nd = p.nd, m = s.m;
     const size_t B = (size_t)s.B;
     const bool dsm = (a.flags & MTG_FLAG_DS_MEAN) != 0;
@@ -317,13 +319,18 @@ k_lbfgs_persist(const __grid_constant__ Plan pl, const BatchArgs a, const LbfgsS
             loc.has_cand = s.has_cand[b]; loc.n_exp = s.n_exp[b];
         }
         const int ds = b / a.group;
-        if (ds != staged_ds) { k9::stage_series(series, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S); staged_ds = ds; }
-        else __syncthreads();
+        const double *st_t = a.t, *st_y = a.y + ds, *st_d = a.diag + ds;
+        size_t stride = (size_t)a.S;
+        if (lay.stage) {
+            if (ds != staged_ds) { k9::stage_series(series, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S); staged_ds = ds; }
+            else __syncthreads();
+            st_t = series; st_y = series + a.N; st_d = series + 2 * a.N; stride = 1;
+        } else __syncthreads();
         const double dsv = dsm ? a.ds_mean[ds] : 0.0;
         // ---- the problem's remaining L-BFGS loop ----
         for (long long round = 0; round < max_rounds; ++round) {
             int st;
-            const double ll = k9::series_loglike_grad<JR, JC, DUAL>(pl, loc.XT, a.N, series, series + a.N, series + 2 * a.N, dsm, dsv,
+            const double ll = k9::series_loglike_grad<JR, JC, DUAL>(pl, loc.XT, a.N, st_t, st_y, st_d, stride, dsm, dsv,
                                                                     sc, gs, tape, &st, loc.GT);
             if (tid == 0) {
                 loc.LL = ll; loc.k2_status = st;
@@ -353,17 +360,21 @@ template <int JR, int JC, bool DUAL>
 static int launch_persist_one(const Plan &pl, const BatchArgs &a, const LbfgsState &s, const LbfgsParams &p, const int32_t *list,
                               const int32_t *count, int32_t *cursor, int bound, long long max_rounds, cudaStream_t stream)
 {
-    const size_t dyn = mtg_k11_smem_bytes(pl, a.N);
+    const K11Layout lay = mtg_k11_layout(JR + 2 * JC, a.N);
     auto kern = k_lbfgs_persist<JR, JC, DUAL>;
-    MTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K11_SMEM_LIMIT));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = bound < sms ? bound : sms;
     MTG_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t), stream));
-    kern<<<grid, K9_THREADS, dyn, stream>>>(pl, a, s, p, list, count, cursor, max_rounds);
+    double *scratch = nullptr;
+    if (lay.scratch_doubles) MTG_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * lay.scratch_doubles * (size_t)grid, stream));
+    kern<<<grid, K9_THREADS, lay.dyn_bytes, stream>>>(pl, a, s, p, list, count, cursor, max_rounds, lay, scratch);
     mtg_count_launch();
-    return mtg_cuda_check(cudaGetLastError(), "k_lbfgs_persist launch");
+    int rc = mtg_cuda_check(cudaGetLastError(), "k_lbfgs_persist launch");
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return rc;
 }
 template <int JR, int JC>
 static int launch_persist(const Plan &pl, const BatchArgs &a, const LbfgsState &s, const LbfgsParams &p, const int32_t *list,

@@ -11,14 +11,15 @@ namespace k9 {
 
 template <int JR, int JC, bool DUAL>
 __global__ void __launch_bounds__(K9_THREADS, 1)
-k11_loglike_grad_scan(const __grid_constant__ Plan pl, const BatchArgs a)
+k11_loglike_grad_scan(const __grid_constant__ Plan pl, const BatchArgs a, const K11Layout lay, double *__restrict__ scratch)
 {
     constexpr int J = JR + 2 * JC;
     __shared__ Scratch<J> sc;
     __shared__ GScratch<JR, JC, DUAL> gs;
     __shared__ double xs[MTG_MAX_PARAMS], gsm[MTG_MAX_PARAMS];
-    extern __shared__ double k11_dyn[];               // [3][N] series, then the tape
-    double *series = k11_dyn, *tape = k11_dyn + 3 * (size_t)a.N;
+    extern __shared__ double k11_dyn[];               // [3][N] series when staged, then the tape when it fits
+    double *series = k11_dyn;
+    double *tape = lay.tape_smem ? k11_dyn + (lay.stage ? 3 * (size_t)a.N : 0) : scratch + (size_t)blockIdx.x * lay.scratch_doubles;
     const int nd = pl.n_free, tid = threadIdx.x;
     const int nwork = a.count ? min(a.B, *a.count) : a.B;
     const bool dsm = (a.flags & MTG_FLAG_DS_MEAN) != 0;
@@ -28,11 +29,16 @@ k11_loglike_grad_scan(const __grid_constant__ Plan pl, const BatchArgs a)
         const int ds = b / a.group;
         __syncthreads();                              // previous series done with xs / gsm / the staged data
         if (tid < nd) xs[tid] = a.params[(size_t)b * nd + tid];
-        if (ds != staged_ds) { stage_series(series, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S); staged_ds = ds; }
-        else __syncthreads();
+        const double *st_t = a.t, *st_y = a.y + ds, *st_d = a.diag + ds;
+        size_t stride = (size_t)a.S;
+        if (lay.stage) {
+            if (ds != staged_ds) { stage_series(series, a.N, a.t, a.y + ds, a.diag + ds, (size_t)a.S); staged_ds = ds; }
+            else __syncthreads();
+            st_t = series; st_y = series + a.N; st_d = series + 2 * a.N; stride = 1;
+        } else __syncthreads();
         const bool inside = !(a.flags & MTG_FLAG_APPLY_PRIOR) || plan_in_prior(pl, xs);
         int st;
-        double ll = series_loglike_grad<JR, JC, DUAL>(pl, xs, a.N, series, series + a.N, series + 2 * a.N, dsm, dsm ? a.ds_mean[ds] : 0.0,
+        double ll = series_loglike_grad<JR, JC, DUAL>(pl, xs, a.N, st_t, st_y, st_d, stride, dsm, dsm ? a.ds_mean[ds] : 0.0,
                                                       sc, gs, tape, &st, gsm);
         if (!inside) { ll = -INFINITY; st = 3; }
         if (tid == 0) { a.out_ll[b] = ll; if (a.status) a.status[b] = st; }
@@ -42,19 +48,11 @@ k11_loglike_grad_scan(const __grid_constant__ Plan pl, const BatchArgs a)
 
 }  // namespace k9
 
-// dynamic shared memory of one K11 CTA: the staged series and the (m, P) tape
-size_t mtg_k11_smem_bytes(const Plan &pl, int N)
-{
-    const int J = pl.jr + 2 * pl.jc;
-    const size_t KT = (size_t)J + (size_t)J * (J + 1) / 2;
-    const size_t CH = ((size_t)N + K9_THREADS - 1) / K9_THREADS;
-    return sizeof(double) * (3 * (size_t)N + KT * CH * K9_THREADS);
-}
-#define K11_SMEM_LIMIT (200 * 1024)          // of the 227 KB an sm_100a CTA may use; the rest is static scratch
-
+// every model the scan covers (<= 4 state dimensions), any series length: the series is staged in shared memory up to
+// K9_STAGE_MAX_N points and the tape lives in shared memory while it fits, in a per-CTA global scratch beyond (mtg_k11_layout)
 bool mtg_k11_supports(const Plan &pl, int N)
 {
-    return mtg_k9_supports(pl) && N >= 1 && N <= K9_STAGE_MAX_N && mtg_k11_smem_bytes(pl, N) <= K11_SMEM_LIMIT;
+    return mtg_k9_supports(pl) && N >= 1;
 }
 
 static int k11_sms()
@@ -70,13 +68,21 @@ static int k11_sms()
 template <int JR, int JC, bool DUAL>
 static int launch_k11_one(const Plan &pl, const BatchArgs &a, cudaStream_t stream)
 {
-    const size_t dyn = mtg_k11_smem_bytes(pl, a.N);
+    const K11Layout lay = mtg_k11_layout(JR + 2 * JC, a.N);
     auto kern = k9::k11_loglike_grad_scan<JR, JC, DUAL>;
     MTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K11_SMEM_LIMIT));
     const int grid = a.B < k11_sms() ? a.B : k11_sms();          // one CTA per SM (255 registers x 256 threads), grid-stride over the series
-    kern<<<grid, K9_THREADS, dyn, stream>>>(pl, a);
+    double *scratch = nullptr;
+    if (lay.scratch_doubles) {
+        int rc = mtg_pool_setup();
+        if (rc) return rc;
+        MTG_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * lay.scratch_doubles * (size_t)grid, stream));
+    }
+    kern<<<grid, K9_THREADS, lay.dyn_bytes, stream>>>(pl, a, lay, scratch);
     mtg_count_launch();
-    return mtg_cuda_check(cudaGetLastError(), "k11_loglike_grad_scan launch");
+    int rc = mtg_cuda_check(cudaGetLastError(), "k11_loglike_grad_scan launch");
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return rc;
 }
 template <int JR, int JC>
 static int launch_k11(const Plan &pl, const BatchArgs &a, cudaStream_t stream)

@@ -121,8 +121,30 @@ struct GScratch {
     double red[K9_WARPS][GradCount<JR, JC, DUAL>::N];
 };
 
-// shared-memory tape: (m, P) before every step of the thread's chunk; component k of slot i at tape[(i * KT + k) * T + tid]
+// tape: (m, P) before every step of the thread's chunk; component k of slot i at tape[(i * KT + k) * T + tid]
 template <int J> struct TapeDims { static constexpr int KT = J + J * (J + 1) / 2; };
+
+}  // namespace k9
+
+// Where one K11 CTA keeps the series and the tape: both in shared memory when they fit (N <= ~2000 at J = 3), else the tape
+// in a per-CTA global scratch, and for series beyond K9_STAGE_MAX_N points the data is read from global memory as well.
+struct K11Layout { int stage; int tape_smem; size_t dyn_bytes; size_t scratch_doubles; };      // scratch per CTA, in doubles
+#define K11_SMEM_LIMIT (200 * 1024)          // of the 227 KB an sm_100a CTA may use; the rest is static scratch
+static inline K11Layout mtg_k11_layout(int J, int N)
+{
+    const size_t KT = (size_t)J + (size_t)J * (J + 1) / 2;
+    const size_t CH = ((size_t)N + K9_THREADS - 1) / K9_THREADS;
+    const size_t series = sizeof(double) * 3 * (size_t)N, tape = sizeof(double) * KT * CH * K9_THREADS;
+    K11Layout L;
+    L.stage = N <= K9_STAGE_MAX_N;
+    const size_t base = L.stage ? series : 0;
+    L.tape_smem = base + tape <= K11_SMEM_LIMIT;
+    L.dyn_bytes = base + (L.tape_smem ? tape : 0);
+    L.scratch_doubles = L.tape_smem ? 0 : KT * CH * K9_THREADS;
+    return L;
+}
+
+namespace k9 {
 
 // X <- X F  (J x J row-major times the block-diagonal transition)
 template <int JR, int JC, bool DUAL>
@@ -163,11 +185,13 @@ __device__ __forceinline__ void left_t(const typename Model<JR, JC, DUAL>::Trans
 }
 
 // log-likelihood and gradient of ONE series by the whole CTA (K9_THREADS threads; every thread calls it and gets the
-// log-likelihood back; thread 0 writes grad[0 .. n_free), zeros when *st != 0).  t / yp / dp: the series staged in shared
-// memory (unit stride).  tape: TapeDims<J>::KT * CH * K9_THREADS doubles of shared memory, CH = ceil(N / K9_THREADS).
+// log-likelihood back; thread 0 writes grad[0 .. n_free), zeros when *st != 0).  t / yp / dp: the series, generic pointers --
+// its shared-memory copy (S = 1) or global memory (yp, dp strided by S).  tape: TapeDims<J>::KT * CH * K9_THREADS doubles,
+// CH = ceil(N / K9_THREADS), in shared memory when it fits and in a per-CTA global scratch otherwise (long series: written
+// and read once per evaluation, coalesced over the threads; it stays in L2).
 template <int JR, int JC, bool DUAL>
 __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const double *__restrict__ x, int N, const double *__restrict__ t,
-                                                      const double *__restrict__ yp, const double *__restrict__ dp,
+                                                      const double *__restrict__ yp, const double *__restrict__ dp, size_t S,
                                                       bool ds_mean, double ds_mean_value, Scratch<JR + 2 * JC> &sc,
                                                       GScratch<JR, JC, DUAL> &gs, double *__restrict__ tape, int *st,
                                                       double *__restrict__ grad)
@@ -192,7 +216,7 @@ __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const doub
     // ---- forward: chunk-start state from the scan, then the chunk itself ----------------------------------------
     Elem<J> e;
     e.identity();
-    scan_prefix<JR, JC, DUAL, true>(m, mean, N, t, yp, dp, 1, sc, e.b, e.C);
+    scan_prefix<JR, JC, DUAL, false>(m, mean, N, t, yp, dp, S, sc, e.b, e.C);
     double chi2 = 0.0, prod = 1.0; int esum = 0; bool bad = false;
     for (int n = n0; n < n1; ++n) {
         const int i = n - n0;
@@ -203,7 +227,7 @@ __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const doub
         const double tn = t[n];
         const double dt = n > 0 ? tn - t[n - 1] : 0.0;
         double s, v;
-        append_sv<JR, JC, DUAL>(m, e, dt, yp[n] - mean(tn), dp[n] + m.jit, &s, &v);
+        append_sv<JR, JC, DUAL>(m, e, dt, yp[(size_t)n * S] - mean(tn), dp[(size_t)n * S] + m.jit, &s, &v);
         bad = bad || !(s > 0.0);
         chi2 = fma(v * v, 1.0 / s, chi2);
         prod *= s;
@@ -358,8 +382,8 @@ __device__ __forceinline__ double series_loglike_grad(const Plan &pl, const doub
         for (int k = 0; k < NS; ++k) Pm[k] = Pp[k];
         m.predict_cov(F, Pm);
         m.Ph(Pm, g);
-        const double s = m.hdot(g) + dp[n] + m.jit, rs = 1.0 / s;
-        const double v = yp[n] - mean(tn) - m.hdot(mm);
+        const double s = m.hdot(g) + dp[(size_t)n * S] + m.jit, rs = 1.0 / s;
+        const double v = yp[(size_t)n * S] - mean(tn) - m.hdot(mm);
         // adjoint of the update
         double lg = 0.0, gLg = 0.0, Lg[J];
 #pragma unroll

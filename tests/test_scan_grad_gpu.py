@@ -107,3 +107,34 @@ def test_scan_gradient_status_and_bounds():
         gp7.grad_log_likelihood_batch(y, gp7.get_parameter_vector()[None, :], kernel="scan")
     ll7, g7 = gp7.grad_log_likelihood_batch(y, gp7.get_parameter_vector()[None, :])
     assert np.isfinite(ll7[0]) and np.all(np.isfinite(g7))
+
+
+@pytest.mark.parametrize("N", [2500, 5000, 100000])
+def test_scan_gradient_on_long_series(N):
+    """Beyond what fits an SM's shared memory the tape moves to a per-CTA global scratch (N = 2500 at J = 3), beyond
+    4096 points the series itself is read from global memory (N = 5000), up to the long-baseline size of config C5
+    (N = 1e5): still the complex-step gradient of the celerite recursion."""
+    import bench
+    if N == 100000:
+        t, y, dy = bench.c5_workload(N)
+        day = 86400.0
+        kernel = DampedRandomWalk(-8.0, float(np.log(2 * np.pi / (200 * day))), bounds=[(-30, 10), (-25, 0)]) + \
+            __import__("mind_the_gaps_b200.models", fromlist=["Lorentzian"]).Lorentzian(-9.0, float(np.log(8.0)), float(np.log(2 * np.pi / (7 * day))),
+                                                                                          bounds=[(-30, 10), (-3, 8), (-20, 0)])
+        spec = [("drw",), ("lorentzian",)]
+        B = 2
+    else:
+        t, y, dy, _ = fake_lightcurve(N, 31)
+        kernel, spec = build("drw+lor")
+        B = 6
+    gp = GP(kernel, mean=ConstantModel(float(np.mean(y))), fit_mean=False)
+    gp.compute(t, dy + 1e-12)
+    p0 = gp.get_parameter_vector()
+    p = p0[None, :] + np.random.default_rng(N).normal(0, 0.05, (B, len(p0)))
+    ll, g, status = gp.grad_log_likelihood_batch(y, p, return_status=True, kernel="scan")
+    assert np.all(status == 0)
+    np.testing.assert_allclose(ll, ogp.loglike_params(spec, p, t, y, dy), rtol=1e-10)
+    assert_grad_close(g, ogp.grad_complex_step(spec, p, t, y, dy))
+    ll2, g2 = gp.grad_log_likelihood_batch(y, p, kernel="k2")
+    np.testing.assert_allclose(ll, ll2, rtol=1e-11)
+    assert_grad_close(g, g2, rtol=1e-8)
