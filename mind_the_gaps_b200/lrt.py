@@ -258,6 +258,9 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
 
     def mcmc_refine(model, nd, lo, hi, x_best, f_best, Lc, y, diag, means, rng, sp, purpose, first):
         """max over a short ensemble run around ``x_best`` (Lc, nd); returns (loglike (Lc,), params (Lc, nd)).
+        (Measured, round 2: running the null model's chain on a second stream beside the alternative's does not pay -- two
+        co-resident K8 launches of 1250 ensembles take 0.84 s against 0.58 s one after the other, and started earlier the
+        null chain blocks the persistent L-BFGS kernel of the alternative fits, which needs whole register files.)
         ``first``: global index of the chunk's first simulation -- folded into the Philox key, because the counters only
         carry the ensemble index INSIDE the launch and simulation k of every chunk / rank would otherwise see the same
         split, stretch, partner and accept draws."""
