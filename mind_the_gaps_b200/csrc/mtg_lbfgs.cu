@@ -72,14 +72,21 @@ __global__ void k_lbfgs_init(LbfgsState s, LbfgsParams p, const double *__restri
     list[b] = b;
 }
 
+// loop over the parameters: unrolled with a guard when NDMAX is small (register arrays), a plain loop otherwise
+#define LB_STR2(x) #x
+#define LB_STR(x) LB_STR2(x)
+#define LB_K(k) _Pragma("unroll (NDMAX <= 8 ? NDMAX : 1)") for (int k = 0; k < (NDMAX <= 8 ? NDMAX : nd); ++k) if (NDMAX > 8 || k < nd)
+#define LB_SMALL 8
+
 // new search direction at the current point; returns false if the point is stationary
+template <int NDMAX>
 __device__ bool lbfgs_direction(const LbfgsState &s, const LbfgsParams &p, int b, double *alpha_out)
 {
     const int nd = p.nd, B = s.B;
-    double q[MTG_MAX_PARAMS], g[MTG_MAX_PARAMS];
-    bool fixed[MTG_MAX_PARAMS];
+    double q[NDMAX], g[NDMAX];
+    bool fixed[NDMAX];
     double qq = 0.0;
-    for (int k = 0; k < nd; ++k) {
+    LB_K(k) {
         const double xk = s.X[(size_t)k * B + b];
         g[k] = s.G[(size_t)k * B + b];
         fixed[k] = (xk <= p.lo[k] && g[k] > 0.0) || (xk >= p.hi[k] && g[k] < 0.0);
@@ -90,80 +97,86 @@ __device__ bool lbfgs_direction(const LbfgsState &s, const LbfgsParams &p, int b
     int hn = s.hist_n[b];
     const int head = s.hist_head[b];       // slot of the NEXT write; newest = head-1
     double al[LB_MAXM];
-    double d[MTG_MAX_PARAMS];
-    for (int k = 0; k < nd; ++k) d[k] = q[k];
+    double d[NDMAX];
+    LB_K(k) d[k] = q[k];
     for (int i = 0; i < hn; ++i) {
         const int slot = (head - 1 - i + 2 * s.m) % s.m;
         double sd = 0.0;
-        for (int k = 0; k < nd; ++k) if (!fixed[k]) sd += s.SH[((size_t)slot * nd + k) * B + b] * d[k];
+        LB_K(k) if (!fixed[k]) sd += s.SH[((size_t)slot * nd + k) * B + b] * d[k];
         al[i] = s.RHO[(size_t)slot * B + b] * sd;
-        for (int k = 0; k < nd; ++k) if (!fixed[k]) d[k] -= al[i] * s.YH[((size_t)slot * nd + k) * B + b];
+        LB_K(k) if (!fixed[k]) d[k] -= al[i] * s.YH[((size_t)slot * nd + k) * B + b];
     }
     if (hn > 0) {
         const int slot = (head - 1 + s.m) % s.m;
         double sy = 0.0, yy = 0.0;
-        for (int k = 0; k < nd; ++k) if (!fixed[k]) {
+        LB_K(k) if (!fixed[k]) {
             const double yk = s.YH[((size_t)slot * nd + k) * B + b];
             sy += s.SH[((size_t)slot * nd + k) * B + b] * yk; yy += yk * yk;
         }
         const double gamma = (yy > 0.0 && sy > 0.0) ? sy / yy : 1.0;
-        for (int k = 0; k < nd; ++k) d[k] *= gamma;
+        LB_K(k) d[k] *= gamma;
     }
     for (int i = hn - 1; i >= 0; --i) {
         const int slot = (head - 1 - i + 2 * s.m) % s.m;
         double yd = 0.0;
-        for (int k = 0; k < nd; ++k) if (!fixed[k]) yd += s.YH[((size_t)slot * nd + k) * B + b] * d[k];
+        LB_K(k) if (!fixed[k]) yd += s.YH[((size_t)slot * nd + k) * B + b] * d[k];
         const double be = s.RHO[(size_t)slot * B + b] * yd;
-        for (int k = 0; k < nd; ++k) if (!fixed[k]) d[k] += (al[i] - be) * s.SH[((size_t)slot * nd + k) * B + b];
+        LB_K(k) if (!fixed[k]) d[k] += (al[i] - be) * s.SH[((size_t)slot * nd + k) * B + b];
     }
     double gdir = 0.0;
-    for (int k = 0; k < nd; ++k) { d[k] = fixed[k] ? 0.0 : -d[k]; gdir += g[k] * d[k]; }
+    LB_K(k) { d[k] = fixed[k] ? 0.0 : -d[k]; gdir += g[k] * d[k]; }
     if (!(gdir < 0.0) || !isfinite(gdir)) {          // not a descent direction: steepest descent restart
         hn = 0; s.hist_n[b] = 0;
         gdir = 0.0;
-        for (int k = 0; k < nd; ++k) { d[k] = -q[k]; gdir += g[k] * d[k]; }
+        LB_K(k) { d[k] = -q[k]; gdir += g[k] * d[k]; }
     }
     double alpha = (hn == 0) ? fmin(1.0, 1.0 / sqrt(qq)) : 1.0;
     double dmax = 0.0;
-    for (int k = 0; k < nd; ++k) dmax = fmax(dmax, fabs(d[k]));
+    LB_K(k) dmax = fmax(dmax, fabs(d[k]));
     if (alpha * dmax > p.max_step) alpha = p.max_step / dmax;
-    for (int k = 0; k < nd; ++k) s.Dir[(size_t)k * B + b] = d[k];
+    LB_K(k) s.Dir[(size_t)k * B + b] = d[k];
     s.gd[b] = gdir;
     *alpha_out = alpha;
     return true;
 }
 
+template <int NDMAX>
 __device__ __forceinline__ void lbfgs_set_trial(const LbfgsState &s, const LbfgsParams &p, int b, double alpha)
 {
     const int nd = p.nd, B = s.B;
     s.alpha[b] = alpha;
-    for (int k = 0; k < nd; ++k)
+    LB_K(k)
         s.XT[(size_t)b * nd + k] = clampd(s.X[(size_t)k * B + b] + alpha * s.Dir[(size_t)k * B + b], p.lo[k], p.hi[k]);
 }
 
 // one transition of problem b's state machine after its trial point was evaluated (LL, GT, k2_status hold the result);
-// returns true when the problem is finished (status / flags written)
+// returns true when the problem is finished (status / flags written).
+// NDMAX: compile-time bound on the number of parameters.  NDMAX <= 8: every per-parameter array lives in registers and the
+// loops are unrolled (guarded by k < nd) -- in the persistent kernel this update is a SERIAL section on one thread while
+// 255 wait at a barrier (ncu r02c: 43 % of its stall samples), and the generic form spends it in local-memory traffic and
+// loop overhead; NDMAX = MTG_MAX_PARAMS: the generic form.
+template <int NDMAX>
 __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
 {
     const int nd = p.nd, B = s.B;
     double ft = -s.LL[b];
     if (s.k2_status[b] != 0 || !isfinite(ft)) ft = INFINITY;
-    double gt[MTG_MAX_PARAMS], xt[MTG_MAX_PARAMS];
-    for (int k = 0; k < nd; ++k) { gt[k] = -s.GT[(size_t)b * nd + k]; xt[k] = s.XT[(size_t)b * nd + k]; }
+    double gt[NDMAX], xt[NDMAX];
+    LB_K(k) { gt[k] = -s.GT[(size_t)b * nd + k]; xt[k] = s.XT[(size_t)b * nd + k]; }
     bool done = false; int status = 1;
     bool need_dir = false;
 
     if (s.phase[b] == 0) {
-        if (!isfinite(ft)) { done = true; status = 2; for (int k = 0; k < nd; ++k) s.X[(size_t)k * B + b] = xt[k]; s.F[b] = ft; }
+        if (!isfinite(ft)) { done = true; status = 2; LB_K(k) s.X[(size_t)k * B + b] = xt[k]; s.F[b] = ft; }
         else {
-            for (int k = 0; k < nd; ++k) { s.X[(size_t)k * B + b] = xt[k]; s.G[(size_t)k * B + b] = gt[k]; }
+            LB_K(k) { s.X[(size_t)k * B + b] = xt[k]; s.G[(size_t)k * B + b] = gt[k]; }
             s.F[b] = ft; s.phase[b] = 1; need_dir = true;
         }
     } else {
         const double F = s.F[b];
         const bool armijo_at = [&]() {
             double gdx = 0.0;
-            for (int k = 0; k < nd; ++k) gdx += s.G[(size_t)k * B + b] * (xt[k] - s.X[(size_t)k * B + b]);
+            LB_K(k) gdx += s.G[(size_t)k * B + b] * (xt[k] - s.X[(size_t)k * B + b]);
             return isfinite(ft) && ft <= F + 1e-4 * gdx;
         }();
         // expansion test (weak Wolfe curvature condition): the slope along the direction at the trial point is still
@@ -173,7 +186,7 @@ __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
             if (s.n_exp[b] >= LB_MAX_EXPAND) return false;
             const double a0 = s.alpha[b];
             double slope = 0.0, dmax = 0.0;
-            for (int k = 0; k < nd; ++k) {
+            LB_K(k) {
                 const double dk = s.Dir[(size_t)k * B + b];
                 if (dk != 0.0 && (xt[k] <= p.lo[k] || xt[k] >= p.hi[k])) return false;
                 slope += gt[k] * dk; dmax = fmax(dmax, fabs(dk));
@@ -184,20 +197,20 @@ __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
         // make (xa, fa, ga) the new iterate: history update, convergence tests
         auto accept = [&](const double *xa, double fa, const double *ga) {
             double ss = 0.0, yy = 0.0, sy = 0.0;
-            double dx[MTG_MAX_PARAMS], dg[MTG_MAX_PARAMS];
-            for (int k = 0; k < nd; ++k) {
+            double dx[NDMAX], dg[NDMAX];
+            LB_K(k) {
                 dx[k] = xa[k] - s.X[(size_t)k * B + b]; dg[k] = ga[k] - s.G[(size_t)k * B + b];
                 ss += dx[k] * dx[k]; yy += dg[k] * dg[k]; sy += dx[k] * dg[k];
             }
             if (sy > 1e-10 * sqrt(ss) * sqrt(yy) && sy > 0.0) {
                 const int slot = s.hist_head[b];
-                for (int k = 0; k < nd; ++k) { s.SH[((size_t)slot * nd + k) * B + b] = dx[k]; s.YH[((size_t)slot * nd + k) * B + b] = dg[k]; }
+                LB_K(k) { s.SH[((size_t)slot * nd + k) * B + b] = dx[k]; s.YH[((size_t)slot * nd + k) * B + b] = dg[k]; }
                 s.RHO[(size_t)slot * B + b] = 1.0 / sy;
                 s.hist_head[b] = (slot + 1) % s.m;
                 if (s.hist_n[b] < s.m) s.hist_n[b] += 1;
             }
             double pg = 0.0;
-            for (int k = 0; k < nd; ++k) {
+            LB_K(k) {
                 s.X[(size_t)k * B + b] = xa[k]; s.G[(size_t)k * B + b] = ga[k];
                 pg = fmax(pg, fabs(xa[k] - clampd(xa[k] - ga[k], p.lo[k], p.hi[k])));
             }
@@ -210,9 +223,9 @@ __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
             else need_dir = true;
         };
         auto store_candidate_and_expand = [&]() {
-            for (int k = 0; k < nd; ++k) { s.XC[(size_t)k * B + b] = xt[k]; s.GC[(size_t)k * B + b] = gt[k]; }
+            LB_K(k) { s.XC[(size_t)k * B + b] = xt[k]; s.GC[(size_t)k * B + b] = gt[k]; }
             s.FC[b] = ft; s.has_cand[b] = 1; s.n_exp[b] += 1;
-            lbfgs_set_trial(s, p, b, LB_EXPAND * s.alpha[b]);
+            lbfgs_set_trial<NDMAX>(s, p, b, LB_EXPAND * s.alpha[b]);
         };
         if (s.has_cand[b]) {
             // this evaluation was an expansion trial; the stored candidate already satisfies Armijo
@@ -220,8 +233,8 @@ __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
                 if (wants_expansion()) store_candidate_and_expand();
                 else accept(xt, ft, gt);
             } else {
-                double xc[MTG_MAX_PARAMS], gc[MTG_MAX_PARAMS];
-                for (int k = 0; k < nd; ++k) { xc[k] = s.XC[(size_t)k * B + b]; gc[k] = s.GC[(size_t)k * B + b]; }
+                double xc[NDMAX], gc[NDMAX];
+                LB_K(k) { xc[k] = s.XC[(size_t)k * B + b]; gc[k] = s.GC[(size_t)k * B + b]; }
                 accept(xc, s.FC[b], gc);
             }
         } else if (armijo_at) {
@@ -240,14 +253,14 @@ __device__ bool lbfgs_advance(const LbfgsState &s, const LbfgsParams &p, int b)
                     if (den > 0.0) an = -gd * a0 * a0 / den;
                     an = fmin(fmax(an, 0.1 * a0), 0.5 * a0);
                 }
-                lbfgs_set_trial(s, p, b, an);
+                lbfgs_set_trial<NDMAX>(s, p, b, an);
             }
         }
     }
     if (need_dir) {
         double alpha;
-        if (!lbfgs_direction(s, p, b, &alpha)) { done = true; status = 0; }
-        else { s.ls_count[b] = 0; s.n_exp[b] = 0; s.has_cand[b] = 0; lbfgs_set_trial(s, p, b, alpha); }
+        if (!lbfgs_direction<NDMAX>(s, p, b, &alpha)) { done = true; status = 0; }
+        else { s.ls_count[b] = 0; s.n_exp[b] = 0; s.has_cand[b] = 0; lbfgs_set_trial<NDMAX>(s, p, b, alpha); }
     }
     if (done) { s.status[b] = status; s.flags[b] = 0; }
     return done;
@@ -258,7 +271,8 @@ __global__ void k_lbfgs_update(LbfgsState s, LbfgsParams p, const int32_t *__res
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *count) return;
-    lbfgs_advance(s, p, list[i]);
+    if (p.nd <= LB_SMALL) lbfgs_advance<LB_SMALL>(s, p, list[i]);
+    else lbfgs_advance<MTG_MAX_PARAMS>(s, p, list[i]);
 }
 
 // ---- the persistent tail kernel -------------------------------------------------------------------------------------------
@@ -334,7 +348,7 @@ k_lbfgs_persist(const __grid_constant__ Plan pl, const BatchArgs a, const LbfgsS
                                                                     sc, gs, tape, &st, loc.GT);
             if (tid == 0) {
                 loc.LL = ll; loc.k2_status = st;
-                done_flag = lbfgs_advance(ls, p, 0) ? 1 : 0;
+                done_flag = (nd <= LB_SMALL ? lbfgs_advance<LB_SMALL>(ls, p, 0) : lbfgs_advance<MTG_MAX_PARAMS>(ls, p, 0)) ? 1 : 0;
             }
             __syncthreads();
             if (done_flag) break;

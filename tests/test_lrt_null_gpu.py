@@ -94,7 +94,7 @@ def test_wide_band_null_distribution_matches_cpu_refits_statistically():
     """The bench / tutorial configuration: log_omega0 free over 7 e-folds (~10^3 independent frequencies for this window).
     Two local optimisers started from the same 8 points end in different local maxima for many simulations -- in both
     directions -- so agreement is (i) exact for the null fits, (ii) statistical for T: same distribution (KS), same
-    median, neither procedure systematically better; and (iii) every device optimum is a genuine local maximum: scipy
+    median, the device never the systematically worse; and (iii) every device optimum is a genuine local maximum: scipy
     restarted there cannot improve it."""
     lc, res, Y, DY, l0, l1, b1 = _device_vs_cpu(B_LOR, n_sims=200, seed=11, ns1=8)
     np.testing.assert_allclose(res.loglike_null, l0, rtol=1e-9, atol=1e-6)
@@ -102,7 +102,9 @@ def test_wide_band_null_distribution_matches_cpu_refits_statistically():
     assert ks_2samp(res.T, T_cpu).pvalue > 0.01
     assert abs(np.median(res.T) - np.median(T_cpu)) < 0.8
     better_dev, better_cpu = np.mean(res.T > T_cpu + 1e-3), np.mean(T_cpu > res.T + 1e-3)
-    assert abs(better_dev - better_cpu) < 0.2, (better_dev, better_cpu)
+    # measured: device better 32-39 %, CPU better 19-29 % (it moves with the rounding of the optimiser's arithmetic): the
+    # device procedure must not be the systematically worse one
+    assert better_cpu < better_dev + 0.15, (better_dev, better_cpu)
     spec = [("lorentzian",), ("drw",)]
     gain = np.empty(40)
     for k, i in enumerate(range(0, 200, 5)):
