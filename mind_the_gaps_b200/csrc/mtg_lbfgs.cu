@@ -12,7 +12,7 @@
 // The host only launches rounds and reads the active count every few rounds.
 //
 // TAIL: a K2 round costs ~1.1 ms at N = 1000 whatever the batch, and most rounds of a batched fit serve a few hundred slowly
-// converging problems.  Once the active count drops below MTG_LBFGS_SWITCH (default: about what makes one pass of the
+// converging problems.  Once the active count drops below MTG_LBFGS_SWITCH (default 6144: about what makes one pass of the
 // persistent kernel over the active problems as cheap as one K2 round) the remaining problems are handed to ONE launch of
 // k_lbfgs_persist: every CTA takes a problem from a work queue, copies its optimiser state into shared memory and
 // runs its whole remaining L-BFGS loop there -- gradient by the parallel-in-time kernel K11 (series_loglike_grad, ~30 us),
@@ -410,7 +410,7 @@ static int persist_dispatch(const Plan &pl, const BatchArgs &a, const LbfgsState
 static int lbfgs_switch_count()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("MTG_LBFGS_SWITCH"); v = e ? atoi(e) : 4096; }
+    if (v < 0) { const char *e = getenv("MTG_LBFGS_SWITCH"); v = e ? atoi(e) : 6144; }
     return v;
 }
 
