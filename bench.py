@@ -105,6 +105,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def k1_profile_traffic():
+    """DRAM bytes per launch of the headline kernel from the committed ncu capture (profiles/r02c_k1_ncu_full_raw.csv:
+    header row, unit row, value row); None when the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02c_k1_ncu_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        head, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = head.index(key)
+            tot += float(vals[i].replace(",", "")) * scale[units[i]]
+        return tot, "profiles/r02c_k1_ncu_full_raw.csv"
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -675,6 +693,7 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        k1_traffic = k1_profile_traffic()
         alg_bytes = B * (5 * 8 + 8 + 4) + 3 * N_POINTS * 8
         line = {
             "metric": "celerite loglike evals/s (N=1k, J=4)", "value": value, "unit": "evals/s",
@@ -693,9 +712,9 @@ def main():
             "gpu_launches": kernel_launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": pk_value, "unit": "TFLOP/s",
                          "frac": achieved_tf / pk_value if pk_value else None,
-                         "traffic": 15287808 * (B / 378880.0), "traffic_unit": "bytes per launch (dram read+write)",
-                         "traffic_source": "profiles/r01j_k1_ncu_full_raw.csv (ncu --set full, 378880 series: dram__bytes_read 15.29 MB, "
-                                           "dram__bytes_write 0), scaled to this batch",
+                         "traffic": k1_traffic[0] * (B / 378880.0) if k1_traffic else None, "traffic_unit": "bytes per launch (dram read+write)",
+                         "traffic_source": ("%s (ncu --set full of this kernel at 378880 series: dram__bytes_read.sum + "
+                                            "dram__bytes_write.sum = %.2f MB), scaled to this batch" % (k1_traffic[1], k1_traffic[0] / 1e6)) if k1_traffic else None,
                          "kernel": "k1_loglike<1,1,false,true>",
                          "flops_per_eval": FLOPS_PER_EVAL_COMPUTE,
                          "flops_model": "N (4 J^2 + 12 J + 5) at the J = 3 the kernel executes (SURVEY.md 8d formula)",
