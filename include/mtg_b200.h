@@ -216,6 +216,11 @@ int mtg_sim_destroy(void *sim);
  * un-padded grid lengths) for the next simulator of the same FFT length on the same device; at most MTG_SIM_POOL
  * (environment, default 4, 0 disables) workspaces are kept.  mtg_sim_trim releases them. */
 int mtg_sim_trim(void);
+/* 1 when this simulator's binned Gaussian-PDF lightcurves come from the fused synthesis + binning kernels
+ * (csrc/mtg_tk95.cu: n_fft = 2^p x N2 and a window sparse enough that only a fraction of the series is needed), 0 when
+ * they come from the spectrum -> cuFFT -> binning chain.  Environment MTG_SIM_FUSED = 0 | 1 (default) | 2 (whenever the
+ * grid factorises), read by mtg_sim_create. */
+int mtg_sim_is_fused(void *sim);
 
 /* Generate L noiseless binned lightcurves.
  * PSD source: `model` + params[L][n_free] (celerite kernel PSD evaluated on the device, the

@@ -98,6 +98,7 @@ SIGNATURES = {
     "mtg_sim_create": (ctypes.c_int, [ctypes.POINTER(MtgSimConfig), ctypes.POINTER(ctypes.c_void_p)]),
     "mtg_sim_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mtg_sim_trim": (ctypes.c_int, []),
+    "mtg_sim_is_fused": (ctypes.c_int, [ctypes.c_void_p]),
     "mtg_power_spectrum_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "mtg_autocorr_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "mtg_lombscargle_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -13,23 +13,7 @@
 #include <mutex>
 #include <vector>
 
-#include "mtg_philox.cuh"
-
-// two uniforms for (stream `purpose`, item, draw)
-__device__ __forceinline__ double2 philox_u2(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
-{
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)(item >> 32), draw, purpose),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    return make_double2(u01_from_bits(r.x, r.y), u01_from_bits(r.z, r.w));
-}
-__device__ __forceinline__ double2 philox_normal2(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
-{
-    const double2 u = philox_u2(seed, purpose, item, draw);
-    const double r = sqrt(-2.0 * log(u.x));
-    double s, c;
-    sincospi(2.0 * u.y, &s, &c);
-    return make_double2(r * c, r * s);
-}
+#include "mtg_sim_dev.cuh"
 
 // ---- celerite PSD coefficients for one parameter vector (runtime J) ---------------------------------
 __global__ void k_psd_coeffs(const __grid_constant__ Plan pl, const double *__restrict__ params, int L, PsdCoef *out)
@@ -64,70 +48,6 @@ __global__ void k_psd_coeffs(const __grid_constant__ Plan pl, const double *__re
         c.ac[c.nc] = a; c.bc[c.nc] = b; c.cc[c.nc] = cc; c.dc[c.nc] = d; ++c.nc;
     }
     out[l] = c;
-}
-
-__device__ __forceinline__ double psd_eval(const PsdCoef &c, double w)
-{
-    const double w2 = w * w;
-    double p = 0.0;
-    for (int j = 0; j < c.nr; ++j) p += c.ar[j] * c.cr[j] / (c.cr[j] * c.cr[j] + w2);
-    for (int j = 0; j < c.nc; ++j) {
-        const double a = c.ac[j], b = c.bc[j], cc = c.cc[j], d = c.dc[j];
-        const double w02 = cc * cc + d * d;
-        p += ((a * cc + b * d) * w02 + (a * cc - b * d) * w2) / (w2 * w2 + 2.0 * (cc * cc - d * d) * w2 + w02 * w02);
-    }
-    return 0.79788456080286535588 * p;          // sqrt(2/pi)
-}
-
-// ---- fast helpers for the Philox path of K3 (statistical equivalence only; the injected-noise path keeps IEEE ops) ----
-// Standard normal pair from 128 Philox bits by Box-Muller with FP32 transcendentals.  ln(u1) keeps the full tail of a
-// 64-bit uniform: u1 = 2^-(z+1) * 1.m with z = leading zeros of the 64 random bits (geometric), m the next 23 bits, so
-// -2 ln u1 = 2 ln2 ((z + 1) - log2(1.m)) reaches ~9.4 sigma although every floating-point step is single precision
-// (relative error of a deviate ~1e-7: irrelevant for a random draw, ~6x fewer issue slots than the FP64 libm calls).
-__device__ __forceinline__ float2 philox_normal2_f32(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
-{
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)(item >> 32), draw, purpose),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint64_t bits = ((uint64_t)r.x << 32) | r.y;
-    const int z = bits ? __clzll((long long)bits) : 63;
-    const uint64_t norm = bits << z;                                   // top bit set (or 0)
-    const float mant = __uint_as_float(0x3f800000u | (uint32_t)((norm >> 40) & 0x7fffffu));       // [1, 2)
-    const float neg_log2_u = (float)(z + 1) - __log2f(mant) + 2.0e-8f;                     // > 0
-    const float rad = sqrtf(1.3862943611198906f * neg_log2_u);                              // sqrt(-2 ln u1)
-    const float ang = (float)(r.z >> 8) * 5.9604644775390625e-08f;                          // [0, 1) in steps of 2^-24
-    float sn, cs;
-    sincospif(2.0f * ang + 5.9604644775390625e-08f, &sn, &cs);
-    (void)r.w;
-    return make_float2(rad * cs, rad * sn);
-}
-// 1/x and sqrt(x) for x in the single-precision range from an FP32 seed + two Newton steps (<= 2 ulp); IEEE otherwise
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    if (!(fabs(x) > 1e-30 && fabs(x) < 1e30)) return 1.0 / x;
-    double y = (double)(1.0f / (float)x);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return fma(y, fma(-x, y, 1.0), y);
-}
-__device__ __forceinline__ double fast_sqrt(double x)
-{
-    if (!(x > 1e-30 && x < 1e30)) return sqrt(x);
-    double y = (double)rsqrtf((float)x);                 // ~ 1/sqrt(x)
-    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
-    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
-    const double g = x * y;                              // sqrt(x), then one correction step
-    return fma(0.5 * y, fma(-g, g, x), g);
-}
-__device__ __forceinline__ double psd_eval_fast(const PsdCoef &c, double w)
-{
-    const double w2 = w * w;
-    double p = 0.0;
-    for (int j = 0; j < c.nr; ++j) p += c.ar[j] * c.cr[j] * fast_rcp(c.cr[j] * c.cr[j] + w2);
-    for (int j = 0; j < c.nc; ++j) {
-        const double a = c.ac[j], b = c.bc[j], cc = c.cc[j], d = c.dc[j];
-        const double w02 = cc * cc + d * d;
-        p += ((a * cc + b * d) * w02 + (a * cc - b * d) * w2) * fast_rcp(w2 * w2 + 2.0 * (cc * cc - d * d) * w2 + w02 * w02);
-    }
-    return 0.79788456080286535588 * p;          // sqrt(2/pi)
 }
 
 static inline void spectrum_scales(int n_fft, double sim_dt, double *val, double *fold)
@@ -202,38 +122,6 @@ __global__ void k_segment(int L, int n_fft, const double *__restrict__ grid, dou
     seg[l] = s;
 }
 
-// numpy's pairwise summation (npy pairwise_sum, block 128, 8 accumulators)
-__device__ double np_pairwise_sum(const double *a, int n)
-{
-    if (n < 8) {
-        double res = -0.0;
-        for (int i = 0; i < n; ++i) res += a[i];
-        return res;
-    }
-    if (n <= 128) {
-        double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-            r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
-            r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
-        }
-        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-        for (; i < n; ++i) res += a[i];
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
-}
-// np.mean of the fancy-indexed (k, 1) slice the reference averages (simulator.py:362-364): numpy's
-// add.reduce is the pairwise sum over all k elements, then a true divide by k (verified against
-// numpy 2.3 for k = 1..1000 in tests/test_simulator_gpu.py)
-__device__ __forceinline__ double np_mean(const double *a, int n)
-{
-    if (n <= 0) return nan("");
-    return np_pairwise_sum(a, n) / (double)n;
-}
-
 // first j in [0, len) with (time(j) >= x), time(j) = base[j] + shift, starting from a guess
 template <class TimeFn>
 __device__ __forceinline__ int first_ge(TimeFn time, int len, double x, int guess)
@@ -277,6 +165,34 @@ k_bin(int L, int n_obs, int n_fft, const double *__restrict__ grid, const double
         }
     }
     out_tm[(size_t)n * L_total + l_out0 + l] = r;
+}
+
+// K5c: which samples does every bin of every lightcurve need?  Same membership arithmetic as k_bin; feeds the fused
+// TK95 path (mtg_tk95.cu).  thread -> (l, n) with n fastest.  mslot[l][q_off[n] + i] = absolute sample index or -1.
+__global__ void __launch_bounds__(256)
+k_need(int L, int n_obs, const double *__restrict__ grid, double sim_dt, const SegInfo *__restrict__ seg,
+       const double *__restrict__ bin_lo, const double *__restrict__ bin_hi, const int *__restrict__ q_off, int Qmax,
+       int *__restrict__ mslot, int *__restrict__ cnt_out, int *__restrict__ flag)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)L * n_obs) return;
+    const int l = (int)(idx / n_obs), n = (int)(idx % n_obs);
+    const SegInfo s = seg[l];
+    const int len = s.i1 - s.i0;
+    const double *g = grid + s.i0;
+    const double sh = s.time_shift;
+    auto time = [&](int j) { return g[j] + sh; };
+    const double lo = bin_lo[n], hi = bin_hi[n];
+    const double t0 = time(0);
+    const int j_lo = first_ge(time, len, lo, (int)((lo - t0) / sim_dt));
+    const int j_hi = first_ge(time, len, hi, (int)((hi - t0) / sim_dt) + 1);
+    int cnt = j_hi - j_lo;
+    const int q0 = q_off[n], cap = q_off[n + 1] - q0;
+    if (cnt > cap) { atomicExch(flag, 1); cnt = cap; }
+    if (cnt < 0) cnt = 0;
+    cnt_out[(size_t)l * n_obs + n] = cnt;
+    int *ms = mslot + (size_t)l * Qmax + q0;
+    for (int i = 0; i < cap; ++i) ms[i] = i < cnt ? s.i0 + j_lo + i : -1;
 }
 
 // ---- K7: noise ----------------------------------------------------------------------------------------
@@ -464,6 +380,20 @@ extern "C" int mtg_sim_create(const mtg_sim_config_t *cfg, void **out)
     if (!rc && cfg->bkg_rate_err) rc = upload(&s->d_err, cfg->bkg_rate_err, cfg->n_obs, s->stream);
     if (!rc) rc = mtg_cuda_check(cudaStreamSynchronize(s->stream), "sim create sync");
     s->first_bin_start = cfg->bin_lo[0];
+    if (!rc && cfg->pdf == MTG_PDF_GAUSSIAN) {
+        std::vector<int> q_off;
+        tk_geometry(cfg->n_fft, cfg->n_obs, cfg->bin_lo, cfg->bin_hi, cfg->sim_dt, &s->tk, &q_off);
+        if (s->tk.ok) {
+            std::vector<double2> tw;
+            tk_twiddles(s->tk, &tw);
+            rc = sim_alloc((void **)&s->d_tw, tw.size() * sizeof(double2));
+            if (!rc) rc = mtg_cuda_check(cudaMemcpy(s->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice), "twiddles");
+            if (!rc) rc = sim_alloc((void **)&s->d_qoff, q_off.size() * sizeof(int));
+            if (!rc) rc = mtg_cuda_check(cudaMemcpy(s->d_qoff, q_off.data(), q_off.size() * sizeof(int), cudaMemcpyHostToDevice), "slot offsets");
+            if (!rc) rc = sim_alloc((void **)&s->d_flag, sizeof(int));
+            if (!rc) rc = mtg_cuda_check(cudaMemset(s->d_flag, 0, sizeof(int)), "flag");
+        }
+    }
     s->cfg.grid = s->cfg.bin_lo = s->cfg.bin_hi = s->cfg.exposures = s->cfg.bkg_counts = s->cfg.bkg_rate_err = nullptr;
     if (rc) { mtg_sim_destroy(s); return rc; }
     *out = s;
@@ -481,6 +411,8 @@ struct SimScratch {
     int device = -1, n_fft = 0, cap = 0;
     double2 *d_spec = nullptr; double *d_lc = nullptr; PsdCoef *d_coef = nullptr; SegInfo *d_seg = nullptr;
     std::map<long long, cufftHandle> plans, plans_d2z;
+    int capF = 0, Qmax = 0, n_obs = 0;                      // fused TK95 chunk buffers
+    double2 *d_Y = nullptr; int *d_mslot = nullptr, *d_cnt = nullptr; PsdCoef *d_coefF = nullptr; SegInfo *d_segF = nullptr;
 };
 static std::mutex g_pool_mu;
 static std::vector<SimScratch> g_pool;
@@ -490,11 +422,18 @@ static void scratch_release(SimScratch &w)
     for (auto &kv : w.plans) cufftDestroy(kv.second);
     for (auto &kv : w.plans_d2z) cufftDestroy(kv.second);
     cudaFree(w.d_spec); cudaFree(w.d_lc); cudaFree(w.d_coef); cudaFree(w.d_seg);
+    cudaFree(w.d_Y); cudaFree(w.d_mslot); cudaFree(w.d_cnt); cudaFree(w.d_coefF); cudaFree(w.d_segF);
 }
 static int pool_limit()
 {
     if (const char *e = getenv("MTG_SIM_POOL")) return atoi(e);
     return 4;
+}
+
+extern "C" int mtg_sim_is_fused(void *sim)
+{
+    const Sim *s = (const Sim *)sim;
+    return s && s->tk.ok && s->cfg.pdf == MTG_PDF_GAUSSIAN ? 1 : 0;
 }
 
 extern "C" int mtg_sim_trim(void)
@@ -516,9 +455,11 @@ extern "C" int mtg_sim_destroy(void *p)
     w.n_fft = s->cfg.n_fft; w.cap = s->cap;
     w.d_spec = s->d_spec; w.d_lc = s->d_lc; w.d_coef = s->d_coef; w.d_seg = s->d_seg;
     w.plans.swap(s->plans); w.plans_d2z.swap(s->plans_d2z);
+    w.capF = s->capF; w.Qmax = s->tk.Qmax; w.n_obs = s->cfg.n_obs;
+    w.d_Y = s->d_Y; w.d_mslot = s->d_mslot; w.d_cnt = s->d_cnt; w.d_coefF = s->d_coefF; w.d_segF = s->d_segF;
     if (s->stream) cudaStreamSynchronize(s->stream);
     bool parked = false;
-    if (w.cap > 0 && pool_limit() > 0) {
+    if ((w.cap > 0 || w.capF > 0) && pool_limit() > 0) {
         std::lock_guard<std::mutex> lock(g_pool_mu);
         if ((int)g_pool.size() >= pool_limit()) {           // drop the oldest
             int dev = 0; cudaGetDevice(&dev);
@@ -530,6 +471,7 @@ extern "C" int mtg_sim_destroy(void *p)
     }
     if (!parked) scratch_release(w);
     cudaFree(s->d_grid); cudaFree(s->d_lo); cudaFree(s->d_hi); cudaFree(s->d_exp); cudaFree(s->d_bkg); cudaFree(s->d_err);
+    cudaFree(s->d_tw); cudaFree(s->d_qoff); cudaFree(s->d_flag); cudaFree(s->d_ampt);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -562,21 +504,57 @@ static int sim_chunk(const Sim *s, int L)
     return (int)(n < (size_t)L ? n : (size_t)L);
 }
 
+// adopt a parked workspace of the same FFT length (and window, for the fused buffers) that is large enough
+static bool sim_adopt(Sim *s, int chunk, int chunkF)
+{
+    if (s->cap != 0 || s->capF != 0) return false;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    int dev = 0; cudaGetDevice(&dev);
+    for (size_t i = 0; i < g_pool.size(); ++i) {
+        SimScratch &w = g_pool[i];
+        if (w.device != dev || w.n_fft != s->cfg.n_fft || w.cap < chunk || w.capF < chunkF) continue;
+        if (w.capF > 0 && (w.Qmax != s->tk.Qmax || w.n_obs != s->cfg.n_obs)) continue;
+        s->d_spec = w.d_spec; s->d_lc = w.d_lc; s->d_coef = w.d_coef; s->d_seg = w.d_seg; s->cap = w.cap;
+        s->plans.swap(w.plans); s->plans_d2z.swap(w.plans_d2z);
+        s->d_Y = w.d_Y; s->d_mslot = w.d_mslot; s->d_cnt = w.d_cnt; s->d_coefF = w.d_coefF; s->d_segF = w.d_segF; s->capF = w.capF;
+        g_pool.erase(g_pool.begin() + i);
+        return true;
+    }
+    return false;
+}
+
+// lightcurves per chunk of the fused TK95 path: Y[l][K2][Qmax] (MTG_SIM_FUSED_MB, default 3 GiB)
+static int sim_chunk_fused(const Sim *s, int L)
+{
+    size_t budget = (size_t)3 << 30;
+    if (const char *e = getenv("MTG_SIM_FUSED_MB")) { long v = atol(e); if (v > 0) budget = (size_t)v << 20; }
+    const size_t per = (size_t)s->tk.Qmax * s->tk.K2 * sizeof(double2);
+    size_t n = budget / per;
+    if (n < 1) n = 1;
+    return (int)(n < (size_t)L ? n : (size_t)L);
+}
+
+static int sim_reserve_fused(Sim *s, int chunk)
+{
+    if (chunk <= s->capF) return 0;
+    if (sim_adopt(s, 0, chunk)) return 0;
+    cudaFree(s->d_Y); cudaFree(s->d_mslot); cudaFree(s->d_cnt);
+    s->d_Y = nullptr; s->d_mslot = nullptr; s->d_cnt = nullptr; s->capF = 0;
+    cudaFree(s->d_coefF); cudaFree(s->d_segF); s->d_coefF = nullptr; s->d_segF = nullptr;
+    int rc;
+    if ((rc = sim_alloc((void **)&s->d_Y, (size_t)chunk * s->tk.K2 * s->tk.Qmax * sizeof(double2)))) return rc;
+    if ((rc = sim_alloc((void **)&s->d_mslot, (size_t)chunk * s->tk.Qmax * sizeof(int)))) return rc;
+    if ((rc = sim_alloc((void **)&s->d_cnt, (size_t)chunk * s->cfg.n_obs * sizeof(int)))) return rc;
+    if ((rc = sim_alloc((void **)&s->d_coefF, (size_t)chunk * sizeof(PsdCoef)))) return rc;
+    if ((rc = sim_alloc((void **)&s->d_segF, (size_t)chunk * sizeof(SegInfo)))) return rc;
+    s->capF = chunk;
+    return 0;
+}
+
 static int sim_reserve(Sim *s, int chunk)
 {
     if (chunk <= s->cap) return 0;
-    if (s->cap == 0) {          // adopt a parked workspace of the same FFT length that is large enough
-        std::lock_guard<std::mutex> lock(g_pool_mu);
-        int dev = 0; cudaGetDevice(&dev);
-        for (size_t i = 0; i < g_pool.size(); ++i) {
-            SimScratch &w = g_pool[i];
-            if (w.device != dev || w.n_fft != s->cfg.n_fft || w.cap < chunk) continue;
-            s->d_spec = w.d_spec; s->d_lc = w.d_lc; s->d_coef = w.d_coef; s->d_seg = w.d_seg; s->cap = w.cap;
-            s->plans.swap(w.plans); s->plans_d2z.swap(w.plans_d2z);
-            g_pool.erase(g_pool.begin() + i);
-            return 0;
-        }
-    }
+    if (sim_adopt(s, chunk, 0)) return 0;
     cudaFree(s->d_spec); cudaFree(s->d_lc); cudaFree(s->d_coef); cudaFree(s->d_seg);
     s->d_spec = nullptr; s->d_lc = nullptr; s->d_coef = nullptr; s->d_seg = nullptr; s->cap = 0;
     int rc;
@@ -600,6 +578,42 @@ int sim_generate_core(Sim *s, int L, const mtg_model_t *model, const double *d_p
         int rc = mtg_build_plan(model, &pl);
         if (rc) return rc;
         if (!d_params && pl.n_free > 0) { mtg_set_error("mtg_sim_generate: params missing"); return MTG_EINVAL; }
+    }
+    if (s->tk.ok && s->cfg.pdf == MTG_PDF_GAUSSIAN) {
+        // fused path (mtg_tk95.cu): segment -> needed samples -> column FFTs in shared memory -> row sums + binning
+        const int chunkF = sim_chunk_fused(s, L);
+        int rc = sim_reserve_fused(s, chunkF);
+        if (rc) return rc;
+        double sp_val, sp_fold;
+        spectrum_scales(n_fft, s->cfg.sim_dt, &sp_val, &sp_fold);
+        const double *d_ampt = nullptr;
+        if (d_psd_table && !d_normals) {
+            if (!s->d_ampt && (rc = sim_alloc((void **)&s->d_ampt, sizeof(double) * (size_t)s->tk.K2 * s->tk.N1))) return rc;
+            if ((rc = tk_launch_amp_table(s->tk, sp_fold, d_psd_table, s->d_ampt, stream))) return rc;
+            d_ampt = s->d_ampt;
+        }
+        for (int l0 = 0; l0 < L; l0 += chunkF) {
+            const int Lc = L - l0 < chunkF ? L - l0 : chunkF;
+            if (model) {
+                k_psd_coeffs<<<(Lc + 127) / 128, 128, 0, stream>>>(pl, d_params + (size_t)l0 * pl.n_free, Lc, s->d_coefF);
+                mtg_count_launch();
+            }
+            k_segment<<<(Lc + 127) / 128, 128, 0, stream>>>(Lc, n_fft, s->d_grid, s->cfg.sim_dt, s->cfg.sim_duration,
+                                                           s->first_bin_start, d_useg ? d_useg + l0 : nullptr, seed,
+                                                           (uint64_t)l0, s->d_segF);
+            const long long tot = (long long)Lc * N;
+            k_need<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(Lc, N, s->d_grid, s->cfg.sim_dt, s->d_segF, s->d_lo, s->d_hi,
+                                                                      s->d_qoff, s->tk.Qmax, s->d_mslot, s->d_cnt, s->d_flag);
+            mtg_count_launch(2);
+            if ((rc = tk_launch_columns(s->tk, Lc, sp_val, sp_fold, model ? s->d_coefF : nullptr, d_psd_table, d_ampt,
+                                        d_normals ? d_normals + (size_t)l0 * 2 * M : nullptr, seed, (uint64_t)l0, s->d_tw,
+                                        s->d_mslot, s->d_Y, stream))) return rc;
+            if ((rc = tk_launch_rows(s->tk, Lc, N, s->d_qoff, s->d_mslot, s->d_cnt, s->d_Y, s->cfg.mean, d_out_tm, L, l0, stream))) return rc;
+            if (d_seg_out)
+                MTG_CUDA(cudaMemcpyAsync(d_seg_out + l0, s->d_segF, sizeof(SegInfo) * Lc, cudaMemcpyDeviceToDevice, stream));
+            MTG_CUDA(cudaGetLastError());
+        }
+        return 0;
     }
     const int chunk = sim_chunk(s, L);
     int rc = sim_reserve(s, chunk);
@@ -693,8 +707,11 @@ extern "C" int mtg_sim_generate_host(void *sim, int L, const mtg_model_t *model,
     std::vector<SegInfo> hseg;
     if (!rc && out_seg) { hseg.resize(L); rc = mtg_cuda_check(cudaMemcpyAsync(hseg.data(), d_seg, sizeof(SegInfo) * L, cudaMemcpyDeviceToHost, st), "d2h seg"); }
     if (!rc && out_e13_iters) rc = mtg_cuda_check(cudaMemcpyAsync(out_e13_iters, d_it, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, st), "d2h it");
+    int flag = 0;
+    if (!rc && s->d_flag) rc = mtg_cuda_check(cudaMemcpyAsync(&flag, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st), "d2h flag");
     if (!rc) rc = mtg_cuda_check(cudaStreamSynchronize(st), "sim generate sync");
     else cudaStreamSynchronize(st);
+    if (!rc && flag) { mtg_set_error("fused TK95 path: an exposure bin holds more grid points than the slots reserved for it"); rc = MTG_EINVAL; }
     if (!rc && out_seg) for (int l = 0; l < L; ++l) { out_seg[2 * l] = hseg[l].i0; out_seg[2 * l + 1] = hseg[l].i1 - hseg[l].i0; }
     cudaFree(d_par); cudaFree(d_tab); cudaFree(d_nrm); cudaFree(d_u); cudaFree(d_pv); cudaFree(d_tm); cudaFree(d_rows);
     cudaFree(d_seg); cudaFree(d_it);

@@ -1,0 +1,461 @@
+// mtg_tk95.cu -- K12 / K13: Timmer & Koenig synthesis fused with the exposure binning (sm_100a).
+//
+// Replaces, for Gaussian-PDF simulations whose output is the BINNED lightcurve, the chain
+//   k_spectrum -> cuFFT Z2D (n_fft points) -> k_bin
+// of mtg_sim.cu, i.e. get_fft + np.fft.irfft + downsample of the reference
+// (mind_the_gaps/simulator.py:468-501, :386-393, :340-367).
+//
+// Why: the reference synthesises extension_factor x the observing baseline at min(exposure) / aliasing_factor
+// resolution (n_fft ~ 2.7e6 for config C3 / C4) and then keeps the ~2-3 samples that fall inside each of the N ~ 1000
+// exposures of ONE random segment: 99.9 % of the inverse FFT's output is never read.  cuFFT cannot prune, so the
+// chain above moves ~75 MB (43 MB of it the spectrum and the series, three to five times over inside the library)
+// per lightcurve through HBM.  Here the transform is split as n = N1 x N2 (four-step / Cooley-Tukey,
+// k = N2 k1 + k2, m = m1 + N1 m2):
+//
+//   x[m] = sum_{k2 < N2} w_n^(m k2) A_k2[m mod N1],      A_k2[m1] = sum_{k1 < N1} X[N2 k1 + k2] w_N1^(m1 k1)
+//
+//   K12 k_tk95_columns  one CTA per (lightcurve, column k2): the N1 = 8192 spectrum entries of the column are
+//        GENERATED in shared memory (Philox normals x sqrt(S(w)/2); entries above Nyquist as the conjugate of their
+//        mirror, so every half-spectrum entry is drawn exactly once), transformed there by an in-place radix-8
+//        decimation-in-frequency FFT (padded layout, twiddle tables in shared memory, last 16 points in registers),
+//        and only the entries A_k2[m mod N1] of the <= Qmax samples this lightcurve's segment needs are written:
+//        Y[l][k2][q].  The Hermitian symmetry A_(N2-k2) = w_N1^(-m1) conj(A_k2) halves the columns: K2 = N2/2 + 1.
+//   K13 k_tk95_rows     one thread per needed sample: x = Re sum_k2 c_k2 w_n^(m k2) Y[l][k2][q]  (a length-K2 dot
+//        product with a geometric twiddle; coalesced over q), then the reference's per-bin mean (numpy pairwise order).
+//
+// HBM traffic per lightcurve: ~2 x Q K2 16 B (6-7 MB written and read back for Q ~ 2500, K2 = 165) instead of ~75 MB;
+// the work is bound by the FP64 pipe (FFT butterflies + PSD evaluation) and the integer pipe (Philox).
+// Index work (segment, bin membership) stays in mtg_sim.cu (k_segment, k_need; compiled without FMA contraction).
+#include "mtg_sim_dev.cuh"
+#include <cmath>
+
+#define TK_THREADS 512
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }         // a * i
+
+// y_p = sum_q v_q i^(p q)   (inverse-transform sign)
+__device__ __forceinline__ void dft4(double2 &v0, double2 &v1, double2 &v2, double2 &v3)
+{
+    const double2 e0 = cadd(v0, v2), e1 = cadd(v1, v3), o0 = csub(v0, v2), o1 = cmuli(csub(v1, v3));
+    v0 = cadd(e0, e1); v2 = csub(e0, e1); v1 = cadd(o0, o1); v3 = csub(o0, o1);
+}
+// v_p <- sum_q v_q w8^(p q), w8 = exp(+i pi/4); natural order in and out
+__device__ __forceinline__ void dft8(double2 (&v)[8])
+{
+    const double h = 0.70710678118654752440;
+    double2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+    double2 b0 = csub(v[0], v[4]);
+    const double2 d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+    double2 b1 = make_double2((d1.x - d1.y) * h, (d1.x + d1.y) * h);
+    double2 b2 = cmuli(d2);
+    double2 b3 = make_double2((-d3.x - d3.y) * h, (d3.x - d3.y) * h);
+    dft4(a0, a1, a2, a3);          // even outputs 0, 2, 4, 6
+    dft4(b0, b1, b2, b3);          // odd outputs 1, 3, 5, 7
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
+// padded shared-memory layout: one 16-byte pad per 16 points, so that the register FFT on 16 CONTIGUOUS points
+// (one thread per block of 16) and the strided radix passes are both free of bank conflicts
+__device__ __forceinline__ int tk_phys(int i) { return i + (i >> 4); }
+
+// position of frequency m1 after the DIF passes (digit reversal over the pass radices, natural order in the last block)
+__device__ __forceinline__ int tk_pos(const TkGeom &g, int m1)
+{
+    int pos = 0, shift = g.logN1;
+    for (int s = 0; s < g.npass; ++s) {
+        shift -= g.lograd[s];
+        pos |= (m1 & ((1 << g.lograd[s]) - 1)) << shift;
+        m1 >>= g.lograd[s];
+    }
+    return pos | m1;
+}
+
+// sqrt(x) for x in the single-precision range: FP32 rsqrt seed, one Newton step on 1/sqrt, one correction of the root
+// (error 1e-7 -> 1.5e-14 -> below 1 ulp); IEEE otherwise
+__device__ __forceinline__ double tk_sqrt(double x)
+{
+    if (!(x > 1e-30 && x < 1e30)) return sqrt(x);
+    double y = (double)rsqrtf((float)x);
+    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
+    const double r = x * y;
+    return fma(0.5 * y, fma(-r, r, x), r);
+}
+
+// amplitude table of a host-evaluated PSD in the column order of K12: amp_t[k2][k1] = sqrt(S(w_kk) / 2) * fold with
+// kk = N2 k1 + k2 folded below Nyquist (0 at kk = 0); built once per generate call, read coalesced by every lightcurve
+__global__ void __launch_bounds__(256)
+k_tk95_amp_table(const __grid_constant__ TkGeom g, double fold, const double *__restrict__ psd_table, double *__restrict__ amp_t)
+{
+    const int k1 = blockIdx.x * blockDim.x + threadIdx.x, k2 = blockIdx.y;
+    if (k1 >= g.N1) return;
+    const unsigned k = (unsigned)g.N2 * (unsigned)k1 + (unsigned)k2;
+    const unsigned kk = k > (unsigned)(g.n >> 1) ? (unsigned)g.n - k : k;
+    amp_t[(size_t)k2 * g.N1 + k1] = kk > 0 ? tk_sqrt(0.5 * psd_table[kk]) * fold : 0.0;
+}
+
+// K12.  PARITY: IEEE operations on injected normals (tests); otherwise Philox normals and either the amplitude table
+// (host-evaluated PSD) or the celerite PSD of this lightcurve's parameters.
+// Persistent CTAs, each a CONTIGUOUS range of work items w -> (l, k2) = (w / K2, w % K2): the twiddle tables are loaded
+// once per CTA, the PSD coefficients and the shared-memory positions of the needed samples once per lightcurve.
+template <bool PARITY>
+__global__ void __launch_bounds__(TK_THREADS, 1)
+k_tk95_columns(const __grid_constant__ TkGeom g, int Lc, double val, double fold, const PsdCoef *__restrict__ coefs,
+               const double *__restrict__ psd_table, const double *__restrict__ amp_t, const double *__restrict__ normals,
+               uint64_t seed, uint64_t lc_offset, const double2 *__restrict__ tw_g, const int *__restrict__ mslot,
+               double2 *__restrict__ Y)
+{
+    extern __shared__ __align__(16) double2 tk_smem[];
+    double2 *data = tk_smem;                                     // N1 + N1/16 points
+    double2 *tw = tk_smem + (g.N1 + (g.N1 >> 4) + 1);            // twiddle tables of the passes
+    unsigned short *spos = reinterpret_cast<unsigned short *>(tw + g.tw_total);       // Qmax positions in `data` (0xffff: unused slot)
+    __shared__ PsdCoef sc;
+    const int tid = threadIdx.x;
+    const int N1 = g.N1, n = g.n, M = g.M;
+    const unsigned half = (unsigned)(n >> 1);
+    const double fold2 = fold * fold;
+    for (int i = tid; i < g.tw_total; i += TK_THREADS) tw[i] = tw_g[i];
+    int l_loaded = -1;
+    const long long work = (long long)Lc * g.K2;
+    const long long per = (work + gridDim.x - 1) / gridDim.x;
+    const long long w0 = (long long)blockIdx.x * per, w1 = w0 + per < work ? w0 + per : work;
+    for (long long w = w0; w < w1; ++w) {
+        const int l = (int)(w / g.K2), k2 = (int)(w % g.K2);
+        __syncthreads();                                         // previous item's gather is done with `data`, `spos` and `sc`
+        if (l != l_loaded) {
+            if (coefs && tid < (int)(sizeof(PsdCoef) / sizeof(int)))
+                reinterpret_cast<int *>(&sc)[tid] = reinterpret_cast<const int *>(coefs + l)[tid];
+            const int *ms = mslot + (size_t)l * g.Qmax;
+            for (int q = tid; q < g.Qmax; q += TK_THREADS) {
+                const int m = ms[q];
+                spos[q] = m >= 0 ? (unsigned short)tk_phys(tk_pos(g, m & (N1 - 1))) : (unsigned short)0xffff;
+            }
+            l_loaded = l;
+            if (coefs) __syncthreads();
+        }
+        // ---- generate the column X[N2 k1 + k2], k1 < N1 (natural order) -------------------------------
+        const uint64_t item0 = (lc_offset + (uint64_t)l) * (uint64_t)M;
+        const double *amp_col = amp_t ? amp_t + (size_t)k2 * N1 : nullptr;
+        for (int k1 = tid; k1 < N1; k1 += TK_THREADS) {
+            const unsigned k = (unsigned)g.N2 * (unsigned)k1 + (unsigned)k2;
+            const bool mirror = k > half;
+            const unsigned kk = mirror ? (unsigned)n - k : k;
+            double2 X = make_double2(0.0, 0.0);
+            if (kk > 0) {
+                if (PARITY) {
+                    const double wk = (((double)kk * val) * 2.0) * 3.141592653589793;
+                    const double psd = coefs ? psd_eval(sc, wk) : psd_table[kk];
+                    const double re = normals[((size_t)l * 2) * M + kk], im = normals[((size_t)l * 2 + 1) * M + kk];
+                    const double amp = sqrt(0.5 * psd) * fold;
+                    X.x = re * amp; X.y = im * amp;
+                } else {
+                    const float2 z = philox_normal2_f32(seed, 0u, item0 + kk, 0u);
+                    double amp;
+                    if (amp_col) amp = amp_col[k1];
+                    else {
+                        const double wk = (((double)kk * val) * 2.0) * 3.141592653589793;
+                        amp = tk_sqrt((0.5 * fold2) * psd_eval_fast(sc, wk));
+                    }
+                    X.x = (double)z.x * amp; X.y = (double)z.y * amp;
+                }
+                if (kk == half) X.y = 0.0;                       // Nyquist bin is real (simulator.py:499-500)
+                if (mirror) X.y = -X.y;
+            }
+            data[tk_phys(k1)] = X;
+        }
+        __syncthreads();
+        // ---- in-place decimation-in-frequency passes ------------------------------------------------------
+        int logL = g.logN1;
+        for (int s = 0; s < g.npass; ++s) {
+            const int lr = g.lograd[s], logLs = logL - lr, Ls = 1 << logLs;
+            const double2 *W1 = tw + g.tw_off[s], *W2 = W1 + Ls, *W4 = W2 + Ls;
+            if (lr == 3) {
+                for (int t = tid; t < (N1 >> 3); t += TK_THREADS) {
+                    const int j = t & (Ls - 1), base = ((t >> logLs) << logL) + j;
+                    double2 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = data[tk_phys(base + (q << logLs))];
+                    dft8(v);
+                    const double2 w1 = W1[j], w2 = W2[j], w4 = W4[j];
+                    const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+                    const double2 w7 = cmul(w4, w3);
+                    data[tk_phys(base)] = v[0];
+                    data[tk_phys(base + (1 << logLs))] = cmul(v[1], w1);
+                    data[tk_phys(base + (2 << logLs))] = cmul(v[2], w2);
+                    data[tk_phys(base + (3 << logLs))] = cmul(v[3], w3);
+                    data[tk_phys(base + (4 << logLs))] = cmul(v[4], w4);
+                    data[tk_phys(base + (5 << logLs))] = cmul(v[5], w5);
+                    data[tk_phys(base + (6 << logLs))] = cmul(v[6], w6);
+                    data[tk_phys(base + (7 << logLs))] = cmul(v[7], w7);
+                }
+            } else {                                             // radix 4
+                for (int t = tid; t < (N1 >> 2); t += TK_THREADS) {
+                    const int j = t & (Ls - 1), base = ((t >> logLs) << logL) + j;
+                    double2 v0 = data[tk_phys(base)], v1 = data[tk_phys(base + Ls)];
+                    double2 v2 = data[tk_phys(base + 2 * Ls)], v3 = data[tk_phys(base + 3 * Ls)];
+                    dft4(v0, v1, v2, v3);
+                    const double2 w1 = W1[j], w2 = W2[j];
+                    data[tk_phys(base)] = v0;
+                    data[tk_phys(base + Ls)] = cmul(v1, w1);
+                    data[tk_phys(base + 2 * Ls)] = cmul(v2, w2);
+                    data[tk_phys(base + 3 * Ls)] = cmul(v3, cmul(w1, w2));
+                }
+            }
+            logL = logLs;
+            __syncthreads();
+        }
+        // ---- last F = 8 | 16 contiguous points per thread, in registers, natural order out ----------------------------
+        if (g.F == 16) {
+            for (int t = tid; t < (N1 >> 4); t += TK_THREADS) {
+                double2 *blk = data + t * 17;                    // tk_phys(16 t)
+                double2 a[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double2 lo = blk[q], hi = blk[q + 8];
+                    a[q] = cadd(lo, hi); b[q] = csub(lo, hi);
+                }
+                // b_q *= w16^q
+                const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+                b[1] = cmul(b[1], make_double2(c1, s1));
+                b[2] = make_double2((b[2].x - b[2].y) * h, (b[2].x + b[2].y) * h);
+                b[3] = cmul(b[3], make_double2(s1, c1));
+                b[4] = cmuli(b[4]);
+                b[5] = cmul(b[5], make_double2(-s1, c1));
+                b[6] = make_double2((-b[6].x - b[6].y) * h, (b[6].x - b[6].y) * h);
+                b[7] = cmul(b[7], make_double2(-c1, s1));
+                dft8(a); dft8(b);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { blk[2 * r] = a[r]; blk[2 * r + 1] = b[r]; }
+            }
+        } else {
+            for (int t = tid; t < (N1 >> 3); t += TK_THREADS) {
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = data[tk_phys(8 * t + q)];
+                dft8(v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) data[tk_phys(8 * t + q)] = v[q];
+            }
+        }
+        __syncthreads();
+        // ---- keep what this lightcurve's bins need: Y[l][k2][q] = A_k2[m_q mod N1] ---------------------------
+        double2 *yo = Y + ((size_t)l * g.K2 + k2) * g.Qmax;
+#pragma unroll 4
+        for (int q = tid; q < g.Qmax; q += TK_THREADS) {
+            const unsigned pos = spos[q];
+            if (pos != 0xffffu) yo[q] = data[pos];
+        }
+    }
+}
+
+// K13: grid (ceil(n_obs / TK_BINS_PER_CTA), Lc).  Dynamic shared memory: xs_max doubles.
+__global__ void __launch_bounds__(256)
+k_tk95_rows(const __grid_constant__ TkGeom g, int n_obs, const int *__restrict__ q_off, const int *__restrict__ mslot,
+            const int *__restrict__ cnt, const double2 *__restrict__ Y, double mean_add, double *__restrict__ out_tm,
+            int L_total, int l_out0)
+{
+    extern __shared__ double tk_xs[];
+    const int l = blockIdx.y, b0 = blockIdx.x * TK_BINS_PER_CTA, b1 = min(b0 + TK_BINS_PER_CTA, n_obs);
+    const int q0 = q_off[b0], q1 = q_off[b1];
+    const int *ms = mslot + (size_t)l * g.Qmax;
+    const double2 *yl = Y + (size_t)l * g.K2 * g.Qmax;
+    const bool n2_even = (g.N2 & 1) == 0;
+    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const int m = ms[q];
+        double acc = 0.0;
+        if (m >= 0) {
+            // twiddle w_n^(m k2), k2 = 0, 1, ...: geometric, ratio exp(2 pi i m / n)
+            double sr, cr;
+            sincospi(2.0 * ((double)m / (double)g.n), &sr, &cr);
+            const double2 ratio = make_double2(cr, sr);
+            double2 t;
+            const double2 *yp = yl + q;
+            const size_t ld = (size_t)g.Qmax;
+            const int K2 = g.K2, last = n2_even ? K2 - 1 : K2;          // k2 = 0 (and N2/2 when N2 is even) count once, the rest twice
+            {
+                const double2 a = yp[0];
+                acc = a.x;                                               // t = 1
+                t = ratio;
+            }
+            int k2 = 1;
+            for (; k2 + 8 <= last; k2 += 8) {
+                double2 a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = yp[(size_t)(k2 + u) * ld];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc = fma(2.0, fma(t.x, a[u].x, -t.y * a[u].y), acc);
+                    t = cmul(t, ratio);
+                }
+            }
+            for (; k2 < last; ++k2) {
+                const double2 a = yp[(size_t)k2 * ld];
+                acc = fma(2.0, fma(t.x, a.x, -t.y * a.y), acc);
+                t = cmul(t, ratio);
+            }
+            if (n2_even && K2 > 1) {
+                const double2 a = yp[(size_t)(K2 - 1) * ld];
+                acc += fma(t.x, a.x, -t.y * a.y);
+            }
+        }
+        tk_xs[q - q0] = acc;
+    }
+    __syncthreads();
+    const int b = b0 + threadIdx.x;
+    if (threadIdx.x < TK_BINS_PER_CTA && b < b1) {
+        const int c = cnt[(size_t)l * n_obs + b];
+        const double *src = tk_xs + (q_off[b] - q0);
+        double r;
+        if (c <= 0) r = nan("");
+        else if (mean_add == 0.0) r = np_mean(src, c);
+        else {
+            // countrate - meanrate + mean is applied per sample before averaging (simulator.py:393), as in k_bin
+            double buf[32];
+            if (c <= 32) { for (int i = 0; i < c; ++i) buf[i] = src[i] + mean_add; r = np_mean(buf, c); }
+            else r = np_mean(src, c) + mean_add;
+        }
+        out_tm[(size_t)b * L_total + l_out0 + l] = r;
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+#define TK_SMEM_MAX (225u * 1024u)
+static size_t tk_columns_smem(const TkGeom &g)
+{
+    return sizeof(double2) * ((size_t)g.N1 + (g.N1 >> 4) + 1 + (size_t)g.tw_total) + sizeof(unsigned short) * (((size_t)g.Qmax + 7) & ~(size_t)7);
+}
+static void tk_set_column_length(TkGeom *g, int n_fft, int p)
+{
+    g->n = n_fft; g->logN1 = p; g->N1 = 1 << p; g->N2 = n_fft >> p; g->K2 = g->N2 / 2 + 1; g->M = n_fft / 2 + 1;
+    int L = g->N1, off = 0;
+    g->npass = 0;
+    while (L > 16) {
+        const int lr = L >= 64 ? 3 : 2;
+        g->lograd[g->npass] = lr; g->tw_off[g->npass] = off;
+        L >>= lr;
+        off += (lr == 3 ? 3 : 2) * L;
+        ++g->npass;
+    }
+    g->F = L; g->tw_total = off;
+}
+
+void tk_geometry(int n_fft, int n_obs, const double *bin_lo, const double *bin_hi, double sim_dt, TkGeom *g, std::vector<int> *q_off)
+{
+    TkGeom z{};
+    *g = z;
+    int mode = 1;                       // MTG_SIM_FUSED: 0 never, 1 when it pays (default), 2 whenever the grid factorises (tests)
+    if (const char *e = getenv("MTG_SIM_FUSED")) mode = atoi(e);
+    if (mode == 0 || n_fft < 64 || n_obs < 1) return;
+    int p = 0;
+    while (p < 13 && ((n_fft >> (p + 1)) << (p + 1)) == n_fft) ++p;
+    if (const char *e = getenv("MTG_SIM_FUSED_LOG2N1")) { const int v = atoi(e); if (v >= 3 && v < p) p = v; }      // tests: force a column length
+    if (p < 3) return;
+    tk_set_column_length(g, n_fft, p);
+    // sample slots: a bin of width w holds at most floor(w / dt) + 1 grid points; one more slot absorbs the rounding of the
+    // grid times (k_need flags a bin that would need more)
+    q_off->assign(n_obs + 1, 0);
+    long long tot = 0;
+    double expected = 0.0;
+    for (int b = 0; b < n_obs; ++b) {
+        const double wdt = (bin_hi[b] - bin_lo[b]) / sim_dt;
+        if (!(wdt >= 0.0) || wdt > 1e6) return;
+        tot += (long long)floor(wdt) + 2;
+        expected += wdt + 0.5;
+        if (tot > (1 << 24)) return;
+        (*q_off)[b + 1] = (int)tot;
+    }
+    g->Qmax = (int)tot;
+    int xs = 0;
+    for (int b0 = 0; b0 < n_obs; b0 += TK_BINS_PER_CTA) {
+        const int b1 = b0 + TK_BINS_PER_CTA < n_obs ? b0 + TK_BINS_PER_CTA : n_obs;
+        xs = std::max(xs, (*q_off)[b1] - (*q_off)[b0]);
+    }
+    g->xs_max = xs;
+    if ((size_t)xs * sizeof(double) > 160 * 1024) return;
+    // shared memory of K12: column + twiddle tables + one 16-bit position per slot; shorten the columns until it fits
+    while (tk_columns_smem(*g) > TK_SMEM_MAX && g->logN1 > 3) tk_set_column_length(g, n_fft, g->logN1 - 1);
+    if (tk_columns_smem(*g) > TK_SMEM_MAX) return;
+    // worth it when the entries kept per lightcurve (written once, read once) are fewer bytes than the spectrum + series
+    // the cuFFT chain stores (and moves three to five times)
+    const double fused_bytes = expected * g->K2 * 16.0, chain_bytes = (double)g->M * 16.0 + (double)n_fft * 8.0;
+    if (mode != 2 && fused_bytes > chain_bytes) return;
+    g->ok = 1;
+}
+
+void tk_twiddles(const TkGeom &g, std::vector<double2> *tw)
+{
+    tw->assign(g.tw_total > 0 ? g.tw_total : 1, make_double2(1.0, 0.0));
+    int L = g.N1;
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int s = 0; s < g.npass; ++s) {
+        const int lr = g.lograd[s], Ls = L >> lr, ntab = lr == 3 ? 3 : 2;
+        for (int tab = 0; tab < ntab; ++tab) {
+            const int mult = 1 << tab;                                        // w_L^(j), w_L^(2j), w_L^(4j)
+            for (int j = 0; j < Ls; ++j) {
+                const long double ang = two_pi * (long double)((long long)j * mult) / (long double)L;
+                (*tw)[g.tw_off[s] + tab * Ls + j] = make_double2((double)cosl(ang), (double)sinl(ang));
+            }
+        }
+        L = Ls;
+    }
+}
+
+int tk_launch_amp_table(const TkGeom &g, double fold, const double *psd_table, double *amp_t, cudaStream_t stream)
+{
+    k_tk95_amp_table<<<dim3((g.N1 + 255) / 256, g.K2), 256, 0, stream>>>(g, fold, psd_table, amp_t);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k_tk95_amp_table launch");
+}
+
+int tk_launch_columns(const TkGeom &g, int Lc, double val, double fold, const PsdCoef *coefs, const double *psd_table,
+                      const double *amp_t, const double *normals, uint64_t seed, uint64_t lc_offset, const double2 *tw,
+                      const int *mslot, double2 *Y, cudaStream_t stream)
+{
+    const size_t dyn = tk_columns_smem(g);
+    static bool opted[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int par = normals ? 1 : 0;
+    if (dev < 64 && !opted[dev][par]) {
+        cudaError_t e = par ? cudaFuncSetAttribute(k_tk95_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_MAX)
+                            : cudaFuncSetAttribute(k_tk95_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_MAX);
+        int rc = mtg_cuda_check(e, "k_tk95_columns shared-memory opt-in");
+        if (rc) return rc;
+        opted[dev][par] = true;
+    }
+    static int n_sm[64] = {};
+    if (dev < 64 && n_sm[dev] == 0) cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = dev < 64 && n_sm[dev] > 0 ? n_sm[dev] : 148;
+    const long long work = (long long)Lc * g.K2;
+    const int grid = (int)std::min<long long>(work, (long long)sms);
+    if (par) k_tk95_columns<true><<<grid, TK_THREADS, dyn, stream>>>(g, Lc, val, fold, coefs, psd_table, nullptr, normals, seed, lc_offset, tw, mslot, Y);
+    else     k_tk95_columns<false><<<grid, TK_THREADS, dyn, stream>>>(g, Lc, val, fold, coefs, psd_table, amp_t, normals, seed, lc_offset, tw, mslot, Y);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k_tk95_columns launch");
+}
+
+int tk_launch_rows(const TkGeom &g, int Lc, int n_obs, const int *q_off, const int *mslot, const int *cnt, const double2 *Y,
+                   double mean_add, double *out_tm, int L_total, int l_out0, cudaStream_t stream)
+{
+    const size_t dyn = sizeof(double) * (size_t)std::max(g.xs_max, 1);
+    if (dyn > 48 * 1024) {
+        static bool opted[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 64 && !opted[dev]) {
+            int rc = mtg_cuda_check(cudaFuncSetAttribute(k_tk95_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                    "k_tk95_rows shared-memory opt-in");
+            if (rc) return rc;
+            opted[dev] = true;
+        }
+    }
+    const dim3 grid((n_obs + TK_BINS_PER_CTA - 1) / TK_BINS_PER_CTA, Lc);
+    k_tk95_rows<<<grid, 256, dyn, stream>>>(g, n_obs, q_off, mslot, cnt, Y, mean_add, out_tm, L_total, l_out0);
+    mtg_count_launch();
+    return mtg_cuda_check(cudaGetLastError(), "k_tk95_rows launch");
+}

@@ -83,24 +83,27 @@ class E13Simulator(BaseSimulatorMethod):
         return self.adjust_lightcurve_pdf(segment, self.pdfmethod(self.meanrate, sample_std), max_iter=self.max_iter)
 
 
-def _next_smooth(n):
-    """Smallest 7-smooth integer (2^a 3^b 5^c 7^d) that is >= n."""
-    best = None
-    p7 = 1
-    while p7 < 2 * n:
-        p5 = p7
-        while p5 < 2 * n:
-            p3 = p5
-            while p3 < 2 * n:
-                v = p3
-                while v < n:
-                    v *= 2
-                if best is None or v < best:
-                    best = v
-                p3 *= 3
-            p5 *= 5
-        p7 *= 7
-    return int(best)
+def _largest_prime_factor(v):
+    f, big = 2, 1
+    while f * f <= v:
+        while v % f == 0:
+            big, v = f, v // f
+        f += 1
+    return max(big, v) if v > 1 else big
+
+
+def _fast_length(n):
+    """Smallest ``N1 * N2 >= n`` with ``N1 = 2^p`` (``p <= 13``; ``N2 >= 256`` where ``n`` allows, so the padding stays
+    below half a percent) and no prime factor of ``N2`` above 127.  This is the grid shape of the fused TK95 kernels
+    (``csrc/mtg_tk95.cu``: column FFTs of length ``N1`` in shared memory, a direct sum over ``N2``); the bound on the
+    prime factors keeps cuFFT, which the E13 / regular-lightcurve paths still call on this length, off Bluestein."""
+    n = int(n)
+    p = max(3, min(13, int(np.floor(np.log2(max(n, 2048) / 256.0)))))
+    n1 = 1 << p
+    n2 = -(-n // n1)
+    while _largest_prime_factor(n2) > 127:
+        n2 += 1
+    return n1 * n2
 
 
 _PDF = {"gaussian": _native.PDF_GAUSSIAN, "lognormal": _native.PDF_LOGNORMAL, "uniform": _native.PDF_UNIFORM}
@@ -139,13 +142,16 @@ class Simulator(object):
         self.sim_duration = end_time - start_time
         duration = (times[-1] - times[0]) * extension_factor
         self.sim_timestamps = np.arange(start_time - self.sim_dt, start_time + duration + self.sim_dt, self.sim_dt)
-        if fft_length == "fast":
-            # NOT the reference's behaviour (opt-in): lengthen the regular grid to the next 7-smooth length so
-            # the FFT avoids Bluestein's algorithm; a real window easily gives a prime length
-            n = _next_smooth(len(self.sim_timestamps))
+        if fft_length == "fast" or isinstance(fft_length, (int, np.integer)):
+            # NOT the reference's behaviour (opt-in): lengthen the regular grid to a length the device transforms
+            # without Bluestein's algorithm (a real window easily gives a prime length) -- 2^p x N2, the shape of the
+            # fused synthesis + binning kernels -- or to an explicit length (tests)
+            n = _fast_length(len(self.sim_timestamps)) if fft_length == "fast" else int(fft_length)
+            if n < len(self.sim_timestamps):
+                raise ValueError("fft_length must be at least the reference's grid length %d" % len(self.sim_timestamps))
             self.sim_timestamps = (start_time - self.sim_dt) + np.arange(n) * self.sim_dt
         elif fft_length != "exact":
-            raise ValueError("fft_length must be 'exact' or 'fast'")
+            raise ValueError("fft_length must be 'exact', 'fast' or an explicit length")
         self.fftndatapoints = len(self.sim_timestamps)
         self.pdf = pdf
         self.max_iter = max_iter
@@ -241,6 +247,12 @@ class Simulator(object):
             _native.check(_native.lib().mtg_sim_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._handle = h
         return self._handle
+
+    @property
+    def fused(self):
+        """True when binned Gaussian-PDF lightcurves of this simulator come from the fused synthesis + binning kernels
+        (``csrc/mtg_tk95.cu``) rather than the spectrum -> cuFFT -> binning chain."""
+        return bool(_native.lib().mtg_sim_is_fused(self._sim()))
 
     def _seed(self):
         rs = self.random_state if self.random_state is not None else np.random

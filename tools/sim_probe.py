@@ -20,4 +20,4 @@ for rep in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     rates = sim.generate_lightcurves(n_lc, seed=4)
     torch.cuda.synchronize(); wall = time.perf_counter() - t0
-    print("%d lcs n_fft %d: %.3f s  %.0f lc/s" % (n_lc, sim.fftndatapoints, wall, n_lc / wall), flush=True)
+    print("%d lcs n_fft %d fused %s: %.3f s  %.0f lc/s" % (n_lc, sim.fftndatapoints, sim.fused, wall, n_lc / wall), flush=True)
