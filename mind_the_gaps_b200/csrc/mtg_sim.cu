@@ -62,7 +62,7 @@ static inline void spectrum_scales(int n_fft, double sim_dt, double *val, double
 __global__ void __launch_bounds__(256)
 k_spectrum(int L, int n_fft, int M, double val, double fold, const PsdCoef *__restrict__ coefs,
            const double *__restrict__ psd_table, const double *__restrict__ normals, uint64_t seed,
-           uint64_t lc_offset, double2 *__restrict__ spec)
+           uint64_t lc_offset, int pair_stride, double2 *__restrict__ spec)
 {
     __shared__ PsdCoef sc;
     const int l = blockIdx.y;
@@ -84,7 +84,10 @@ k_spectrum(int L, int n_fft, int M, double val, double fold, const PsdCoef *__re
             out.x = re * amp; out.y = im * amp;
         } else {
             const double psd = coefs ? psd_eval_fast(sc, w) : psd_table[k];
-            const float2 z = philox_normal2_f32(seed, 0u, (lc_offset + l) * (uint64_t)M + k, 0u);
+            const unsigned row = (unsigned)k / (unsigned)pair_stride, col = (unsigned)k - row * (unsigned)pair_stride;
+            float2 ze, zo;
+            spectrum_normals(seed, spectrum_block(lc_offset + l, M, pair_stride, row, col), &ze, &zo);
+            const float2 z = (row & 1u) ? zo : ze;
             const double amp = fast_sqrt(0.5 * psd) * fold;
             out.x = (double)z.x * amp; out.y = (double)z.y * amp;
         }
@@ -628,7 +631,7 @@ int sim_generate_core(Sim *s, int L, const mtg_model_t *model, const double *d_p
         spectrum_scales(n_fft, s->cfg.sim_dt, &sp_val, &sp_fold);
         k_spectrum<<<dim3((M + 255) / 256, Lc), 256, 0, stream>>>(
             Lc, n_fft, M, sp_val, sp_fold, model ? s->d_coef : nullptr, d_psd_table,
-            d_normals ? d_normals + (size_t)l0 * 2 * M : nullptr, seed, (uint64_t)l0, s->d_spec);
+            d_normals ? d_normals + (size_t)l0 * 2 * M : nullptr, seed, (uint64_t)l0, s->tk.N2 > 0 ? s->tk.N2 : 1, s->d_spec);
         mtg_count_launch();
         cufftHandle plan;
         if ((rc = sim_get_plan(s, s->plans, CUFFT_Z2D, n_fft, Lc, &plan))) return rc;
@@ -851,7 +854,7 @@ extern "C" int mtg_sim_regular_host(void *sim, int L, const mtg_model_t *model, 
         double sp_val, sp_fold;
         spectrum_scales(n_fft, s->cfg.sim_dt, &sp_val, &sp_fold);
         k_spectrum<<<dim3((M + 255) / 256, Lc), 256, 0, st>>>(Lc, n_fft, M, sp_val, sp_fold, model ? s->d_coef : nullptr, d_tab,
-                                                              d_nrm, seed, (uint64_t)l0, s->d_spec);
+                                                              d_nrm, seed, (uint64_t)l0, s->tk.N2 > 0 ? s->tk.N2 : 1, s->d_spec);
         cufftHandle plan;
         if ((rc = sim_get_plan(s, s->plans, CUFFT_Z2D, n_fft, Lc, &plan))) break;
         cufftSetStream(plan, st);

@@ -33,26 +33,34 @@ __device__ __forceinline__ double psd_eval(const PsdCoef &c, double w)
     return 0.79788456080286535588 * p;          // sqrt(2/pi)
 }
 
-// ---- fast helpers for the Philox path of K3 (statistical equivalence only; the injected-noise path keeps IEEE ops) ----
-// Standard normal pair from 128 Philox bits by Box-Muller with FP32 transcendentals.  ln(u1) keeps the full tail of a
-// 64-bit uniform: u1 = 2^-(z+1) * 1.m with z = leading zeros of the 64 random bits (geometric), m the next 23 bits, so
-// -2 ln u1 = 2 ln2 ((z + 1) - log2(1.m)) reaches ~9.4 sigma although every floating-point step is single precision
-// (relative error of a deviate ~1e-7: irrelevant for a random draw, ~6x fewer issue slots than the FP64 libm calls).
-__device__ __forceinline__ float2 philox_normal2_f32(uint64_t seed, uint32_t purpose, uint64_t item, uint32_t draw)
+// ---- fast helpers for the Philox path of K3 / K12 (statistical equivalence only; the injected-noise path keeps IEEE ops) ----
+// Standard normal PAIR from 64 random bits by Box-Muller with FP32 / MUFU transcendentals.  The radius uses 40 bits:
+// u1 = 2^-(z+1) * 1.m with z = leading zeros of the field (geometric), m the next 23 bits, so
+// -2 ln u1 = 2 ln2 ((z + 1) - log2(1.m)) reaches 7.4 sigma (P = 1.4e-13 per deviate) although every floating-point step is
+// single precision; the angle uses 24 bits.  Relative error of a deviate ~1e-6: irrelevant for a random draw.
+__device__ __forceinline__ float2 normal_pair_from_bits(uint32_t hi, uint32_t lo)
 {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)(item >> 32), draw, purpose),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint64_t bits = ((uint64_t)r.x << 32) | r.y;
-    const int z = bits ? __clzll((long long)bits) : 63;
+    const uint64_t bits = ((uint64_t)hi << 32) | (lo & 0xff000000u);                    // 40 random bits, left aligned
+    const int z = bits ? __clzll((long long)bits) : 40;
     const uint64_t norm = bits << z;                                   // top bit set (or 0)
     const float mant = __uint_as_float(0x3f800000u | (uint32_t)((norm >> 40) & 0x7fffffu));       // [1, 2)
     const float neg_log2_u = (float)(z + 1) - __log2f(mant) + 2.0e-8f;                     // > 0
-    const float rad = sqrtf(1.3862943611198906f * neg_log2_u);                              // sqrt(-2 ln u1)
-    const float ang = (float)(r.z >> 8) * 5.9604644775390625e-08f;                          // [0, 1) in steps of 2^-24
-    float sn, cs;
-    sincospif(2.0f * ang + 5.9604644775390625e-08f, &sn, &cs);
-    (void)r.w;
-    return make_float2(rad * cs, rad * sn);
+    const float r2 = 1.3862943611198906f * neg_log2_u;                                      // -2 ln u1
+    const float rad = r2 * rsqrtf(r2);
+    const float ang = ((float)(lo & 0xffffffu) - 8388607.5f) * 3.7450704e-07f;              // (-pi, pi) in steps of 2 pi 2^-24
+    return make_float2(rad * __cosf(ang), rad * __sinf(ang));
+}
+// The spectrum stream of the simulator: the half-spectrum entry kk = c + P r (column c < P, row r) of lightcurve `lc`
+// takes half (r & 1) of the Philox block (lc, (r >> 1) P + c): rows 2j and 2j + 1 of a column share one block.  P is the
+// pair stride of the simulator (N2 of the fused geometry, where a thread of K12 owns adjacent rows of a column; 1 otherwise).
+__device__ __forceinline__ uint64_t spectrum_block(uint64_t lc, int M, int P, unsigned r, unsigned c)
+{ return lc * (uint64_t)(M + P) + (uint64_t)(r >> 1) * (uint64_t)P + c; }
+__device__ __forceinline__ void spectrum_normals(uint64_t seed, uint64_t block, float2 *even_row, float2 *odd_row)
+{
+    const uint4 q = philox4x32_10(make_uint4((uint32_t)block, (uint32_t)(block >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    *even_row = normal_pair_from_bits(q.x, q.y);
+    *odd_row = normal_pair_from_bits(q.z, q.w);
 }
 // 1/x and sqrt(x) for x in the single-precision range from an FP32 seed + two Newton steps (<= 2 ulp); IEEE otherwise
 __device__ __forceinline__ double fast_rcp(double x)

@@ -108,8 +108,13 @@ def test_bend_of_bending_powerlaw(pdf, n_sims, max_iter):        # simulator_tes
     ref = _fit_bend(times, _oracle_ensemble(times, 0.2, psd, 10.0, pdf, 30, max_iter, seed=7), variance, bendscale, omega0)
     msg = "device: mean %.3f median %.3f std %.3f | oracle: mean %.3f median %.3f std %.3f | input %.3f" % (
         np.mean(omegas), np.median(omegas), np.std(omegas), np.mean(ref), np.median(ref), np.std(ref), omega0)
-    # the reference's criterion, with the scatter its own algorithm shows (outliers included) as the yardstick
-    assert abs(np.mean(omegas) - omega0) < max(np.std(omegas), np.std(ref)), msg
+    # The reference's criterion (mean within one standard deviation of the input) is not met by the reference's own
+    # algorithm on this window -- the Whittle estimate is biased high by aliasing (oracle: mean ~0.42 for an input of 0.314,
+    # scatter ~0.06) and passes only when a few outlying fits inflate the scatter.  What is asserted instead: the bias of the
+    # device ensemble is the oracle's bias (within 4 standard errors), and the bend is recovered within a factor 1.5.
+    stderr = np.sqrt(np.var(omegas) / len(omegas) + np.var(ref) / len(ref))
+    assert abs(np.mean(omegas) - np.mean(ref)) < 4 * stderr, msg
+    assert omega0 / 1.5 < np.median(omegas) < omega0 * 1.5, msg
     # the distribution of fitted bends is the one the reference's algorithm produces
     assert sps.ks_2samp(omegas, ref).pvalue > 1e-3, msg
 

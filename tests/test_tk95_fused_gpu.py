@@ -101,7 +101,8 @@ def test_fused_equals_cufft_chain_on_the_same_seed_small():
             assert simu.fused == (mode == 2)
             out[mode] = simu.generate_lightcurves(37, seed=1234)
             simu.close()
-    np.testing.assert_allclose(out[2], out[0], rtol=1e-9, atol=1e-9 * np.std(out[0]))
+    # the production kernel stages the generated entries in single precision (a Philox deviate carries no more)
+    np.testing.assert_allclose(out[2], out[0], rtol=2e-6, atol=2e-6 * np.std(out[0]))
 
 
 def test_fused_equals_cufft_chain_at_production_size():
@@ -118,4 +119,29 @@ def test_fused_equals_cufft_chain_at_production_size():
             out[mode] = simu.generate_lightcurves(6, parameters=P, seed=99)
             simu.close()
     assert np.all(np.isfinite(out[1]))
-    np.testing.assert_allclose(out[1], out[0], rtol=1e-9, atol=1e-9 * np.std(out[0]))
+    np.testing.assert_allclose(out[1], out[0], rtol=2e-6, atol=2e-6 * np.std(out[0]))
+
+
+def test_single_role_and_warp_specialised_kernels_agree():
+    """MTG_TK95_WS=0 runs generation and transform back to back in the same warps (double-precision staging)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from helpers import window
+        from mind_the_gaps_b200.models import DampedRandomWalk, Lorentzian
+        from mind_the_gaps_b200.simulator import Simulator
+        t, ex = window(300, 4)
+        k = DampedRandomWalk(np.log(0.01), np.log(2 * np.pi / (20 * 86400.0))) + Lorentzian(np.log(0.005), np.log(30.0), np.log(2 * np.pi / (5 * 86400.0)))
+        s = Simulator(k.get_psd, t, ex, 0.5, extension_factor=2, fft_length="fast")
+        assert s.fused
+        np.save(sys.argv[1], s.generate_lightcurves(9, seed=5))
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for ws in ("0", "1"):
+            f = os.path.join(d, "o%s.npy" % ws)
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, MTG_TK95_WS=ws, MTG_SIM_FUSED="2"), timeout=300)
+            out[ws] = np.load(f)
+    np.testing.assert_allclose(out["1"], out["0"], rtol=2e-6, atol=2e-6 * np.std(out["0"]))
