@@ -115,6 +115,28 @@ __device__ __forceinline__ double tk_amp(const TkPsd &p, double w2)
     return acc > 0.0 ? tk_sqrt_pos(acc) : 0.0;
 }
 
+// the same with the first two real and the first complex term held in registers (the kernels of configs C1-C4)
+struct TkAmpRegs {
+    int nr, nc;
+    double ra0, rc0, ra1, rc1, cA1, cA2, cB1, cB0;
+    __device__ __forceinline__ void load(const TkPsd &p)
+    {
+        nr = p.nr; nc = p.nc;
+        ra0 = nr > 0 ? p.ra[0] : 0.0; rc0 = nr > 0 ? p.rc2[0] : 1.0;
+        ra1 = nr > 1 ? p.ra[1] : 0.0; rc1 = nr > 1 ? p.rc2[1] : 1.0;
+        cA1 = nc > 0 ? p.cA1[0] : 0.0; cA2 = nc > 0 ? p.cA2[0] : 0.0; cB1 = nc > 0 ? p.cB1[0] : 0.0; cB0 = nc > 0 ? p.cB0[0] : 1.0;
+    }
+    __device__ __forceinline__ double amp(const TkPsd &p, double w2) const
+    {
+        double acc = ra0 * tk_rcp_pos(rc0 + w2);
+        if (nr > 1) acc = fma(ra1, tk_rcp_pos(rc1 + w2), acc);
+        if (nc > 0) acc = fma(fma(cA2, w2, cA1), tk_rcp_pos(fma(w2, w2 + cB1, cB0)), acc);
+        for (int j = 2; j < nr; ++j) acc = fma(p.ra[j], tk_rcp_pos(p.rc2[j] + w2), acc);
+        for (int j = 1; j < nc; ++j) acc = fma(fma(p.cA2[j], w2, p.cA1[j]), tk_rcp_pos(fma(w2, w2 + p.cB1[j], p.cB0[j])), acc);
+        return acc > 0.0 ? tk_sqrt_pos(acc) : 0.0;
+    }
+};
+
 // amplitude table of a host-evaluated PSD in the column order of K12: amp_t[k2][k1] = sqrt(S(w_kk) / 2) * fold with
 // kk = N2 k1 + k2 folded below Nyquist (0 at kk = 0); built once per generate call, read coalesced by every lightcurve
 __global__ void __launch_bounds__(256)
@@ -399,6 +421,35 @@ k_tk95_columns_ws(const __grid_constant__ TkGeom g, int Lc, double val, double f
             const uint64_t lcg = lc_offset + (uint64_t)l;
             const double *amp_col = amp_t ? amp_t + (size_t)k2 * N1 : nullptr;
             tk_bar_sync(2, 2 * TK_WS_HALF);                      // FREE: the consumers have read the previous column out of `stage`
+            if (k2 != 0 && N1 >= 4 * TK_WS_HALF) {
+                // Fast path (every column but k2 = 0).  Rows k1 < N1/2 are below Nyquist: entry kk = N2 k1 + k2, stream row k1
+                // of column k2.  Rows k1 >= N1/2 are the conjugates of kk = n - N2 k1 - k2 = N2 (N1 - 1 - k1) + (N2 - k2):
+                // stream row N1 - 1 - k1 of column N2 - k2.  A thread's pair (k1, k1 + 1) shares one Philox block either way;
+                // two pairs per iteration give the integer pipe two independent Philox chains.
+                const uint64_t base_lo = lcg * (uint64_t)(M + g.N2) + (uint64_t)k2, base_hi = lcg * (uint64_t)(M + g.N2) + (uint64_t)(uN2 - (unsigned)k2);
+                TkAmpRegs ar;
+                if (!amp_col) ar.load(ps);
+                auto one_pair = [&](int k1) {
+                    const bool hi = k1 >= (N1 >> 1);
+                    // stream rows of elements k1 (e = 0) and k1 + 1 (e = 1): low half (k1, k1 + 1), high half (N1 - 1 - k1, N1 - 2 - k1)
+                    const unsigned jrow = hi ? (unsigned)(N1 - 2 - k1) >> 1 : (unsigned)k1 >> 1;
+                    float2 ze, zo;
+                    spectrum_normals(seed, (hi ? base_hi : base_lo) + (uint64_t)jrow * (uint64_t)uN2, &ze, &zo);
+                    const unsigned kk0 = hi ? (unsigned)n - (uN2 * (unsigned)k1 + (unsigned)k2) : uN2 * (unsigned)k1 + (unsigned)k2;
+                    const unsigned kk1 = hi ? kk0 - uN2 : kk0 + uN2;
+                    float a0, a1;
+                    if (amp_col) { const double2 a = *reinterpret_cast<const double2 *>(amp_col + k1); a0 = (float)a.x; a1 = (float)a.y; }
+                    else {
+                        const double wa = (double)kk0 * w_scale, wb = (double)kk1 * w_scale;
+                        a0 = (float)ar.amp(ps, wa * wa); a1 = (float)ar.amp(ps, wb * wb);
+                    }
+                    // low half: element 0 sits on an even stream row (ze), element 1 on the odd one; high half: the other way round, conjugated
+                    const float2 z0 = hi ? zo : ze, z1 = hi ? ze : zo;
+                    const float sgn = hi ? -1.f : 1.f;
+                    *reinterpret_cast<float4 *>(stage + k1) = make_float4(z0.x * a0, sgn * z0.y * a0, z1.x * a1, sgn * z1.y * a1);
+                };
+                for (int k1 = 2 * p; k1 < N1; k1 += 4 * TK_WS_HALF) { one_pair(k1); one_pair(k1 + 2 * TK_WS_HALF); }
+            } else {
 #pragma unroll 1
             for (int k1 = 2 * p; k1 < N1; k1 += 2 * TK_WS_HALF) {
                 unsigned kk[2], row[2], col[2]; bool mir[2];
@@ -430,6 +481,7 @@ k_tk95_columns_ws(const __grid_constant__ TkGeom g, int Lc, double val, double f
                 if (kk[0] == 0u) { X.x = 0.f; X.y = 0.f; }
                 if (kk[1] == 0u) { X.z = 0.f; X.w = 0.f; }
                 *reinterpret_cast<float4 *>(stage + k1) = X;
+            }
             }
             __threadfence_block();
             tk_bar_arrive(1, 2 * TK_WS_HALF);                    // FULL
