@@ -190,6 +190,12 @@ int mtg_lbfgs_host(const mtg_model_t *model, int N, int S, int group, int B,
 enum mtg_pdf_kind   { MTG_PDF_GAUSSIAN = 0, MTG_PDF_LOGNORMAL = 1, MTG_PDF_UNIFORM = 2 };
 enum mtg_noise_kind { MTG_NOISE_POISSON = 0, MTG_NOISE_KRAFT = 1, MTG_NOISE_GAUSSIAN = 2 };
 
+/* mtg_sim_config_t.flags.  MTG_SIM_E13_PADDED (set with the lengthened "fast" grid, never on the reference's own grid): the E13
+ * PDF adjustment may run on the segment lengthened to the next 7-smooth length (it needs an FFT pair of the segment's
+ * length per iteration; the window's own length is usually Bluestein territory).  The extra samples come from the same
+ * synthesised series; only the first `duration` of the adjusted segment is binned. */
+#define MTG_SIM_E13_PADDED 1
+
 typedef struct mtg_sim_config {
     int32_t n_obs;              /* N observation bins                                              */
     int32_t n_fft;              /* len(sim_timestamps)            (simulator.py:234-238)           */
@@ -199,7 +205,7 @@ typedef struct mtg_sim_config {
     int32_t pdf;                /* mtg_pdf_kind: Gaussian -> TK95, else E13 (simulator.py:207-214) */
     int32_t max_iter;           /* E13 iterations (default 400)                                    */
     int32_t noise;              /* mtg_noise_kind                 (simulator.py:245-251)           */
-    int32_t reserved;
+    int32_t flags;              /* MTG_SIM_* bits below                                           */
     double  sigma_noise;        /* Gaussian noise sigma                                            */
     double  kraft_counts;       /* Kraft threshold, 15            (noise_models.py:87)             */
     const double *grid;         /* host [n_fft]  sim_timestamps exactly as np.arange produced them */

@@ -53,13 +53,14 @@ class MtgSimConfig(ctypes.Structure):
     """``mtg_sim_config_t``"""
     _fields_ = [("n_obs", ctypes.c_int32), ("n_fft", ctypes.c_int32), ("sim_dt", ctypes.c_double),
                 ("sim_duration", ctypes.c_double), ("mean", ctypes.c_double), ("pdf", ctypes.c_int32),
-                ("max_iter", ctypes.c_int32), ("noise", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("max_iter", ctypes.c_int32), ("noise", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("sigma_noise", ctypes.c_double), ("kraft_counts", ctypes.c_double),
                 ("grid", ctypes.c_void_p), ("bin_lo", ctypes.c_void_p), ("bin_hi", ctypes.c_void_p),
                 ("exposures", ctypes.c_void_p), ("bkg_counts", ctypes.c_void_p), ("bkg_rate_err", ctypes.c_void_p)]
 
 
 PDF_GAUSSIAN, PDF_LOGNORMAL, PDF_UNIFORM = 0, 1, 2
+SIM_E13_PADDED = 1
 NOISE_POISSON, NOISE_KRAFT, NOISE_GAUSSIAN = 0, 1, 2
 
 

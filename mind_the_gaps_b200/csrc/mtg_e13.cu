@@ -29,12 +29,15 @@ __device__ __forceinline__ double e13_u01(uint32_t a, uint32_t b)
 { return ((double)((((uint64_t)a << 32) | b) >> 11) + 0.5) * 1.1102230246251565e-16; }
 
 // gather the segments of the lightcurves listed in `members` into a dense [cnt][n] batch, adding the mean
+// start of the working window of lightcurve l: its segment start, moved back when a padded window would run off the series
+__device__ __forceinline__ int e13_start(const SegInfo &s, int n_fft, int n) { return s.i0 + n <= n_fft ? s.i0 : n_fft - n; }
+
 __global__ void k_e13_gather(const double *__restrict__ lc, int n_fft, const SegInfo *__restrict__ seg,
                              const int *__restrict__ members, int n, double mean, double *__restrict__ dst)
 {
     const int m = blockIdx.y;
-    const int l = members[m];
-    const double *src = lc + (size_t)l * n_fft + seg[l].i0;
+    const int l = members ? members[m] : m;
+    const double *src = lc + (size_t)l * n_fft + e13_start(seg[l], n_fft, n);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         dst[(size_t)m * n + i] = src[i] + mean;
 }
@@ -43,8 +46,8 @@ __global__ void k_e13_scatter_back(double *__restrict__ lc, int n_fft, const Seg
                                    const int32_t *__restrict__ iters, int32_t *__restrict__ iters_out)
 {
     const int m = blockIdx.y;
-    const int l = members[m];
-    double *dst = lc + (size_t)l * n_fft + seg[l].i0;
+    const int l = members ? members[m] : m;
+    double *dst = lc + (size_t)l * n_fft + e13_start(seg[l], n_fft, n);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         dst[i] = src[(size_t)m * n + i];
     if (iters_out && blockIdx.x == 0 && threadIdx.x == 0) iters_out[l] = iters[m];
@@ -122,6 +125,38 @@ __global__ void k_e13_rank_match(const int32_t *__restrict__ perm, const double 
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
         out[(size_t)m * n + perm[(size_t)m * n + r]] = sorted_desc[(size_t)m * n + r];
 }
+// ---- rank order from 32-bit keys ----------------------------------------------------------------------------------
+// The descending argsort of 1.3e6 doubles per lightcurve and iteration was half of K6's time as a 64-bit-key radix sort
+// (8 one-sweep passes over 12-byte pairs).  Rounding to float is monotone, so sorting (float(adj), index) pairs -- 4 passes
+// over 8-byte pairs -- orders everything except runs of EQUAL float keys; k_e13_fix_ties then orders every such run by the
+// double values (insertion sort; runs are 1-3 long for continuous data).  The result is exactly the descending order of the
+// doubles, ties by ascending index.
+__global__ void k_e13_keys32(const double *__restrict__ x, size_t count, float *__restrict__ k)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) k[i] = (float)x[i];
+}
+__global__ void k_e13_fix_ties(const float *__restrict__ k, const double *__restrict__ x, int n, int32_t *__restrict__ perm)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const float kr = k[r];
+        if (r > 0 && k[r - 1] == kr) continue;               // inside a run: its first element does the work
+        int e = r + 1;
+        while (e < n && k[e] == kr) ++e;
+        for (int i = r + 1; i < e; ++i) {
+            const int32_t pi = perm[i];
+            const double vi = x[pi];
+            int j = i - 1;
+            while (j >= r) {
+                const int32_t pj = perm[j];
+                const double vj = x[pj];
+                if (vj > vi || (vj == vi && pj < pi)) break;
+                perm[j + 1] = pj; --j;
+            }
+            perm[j + 1] = pi;
+        }
+    }
+}
+
 // np.allclose(a, b, rtol=1e-4, atol=1e-8): notclose[m] = any(|a-b| > atol + rtol |b|)
 __global__ void k_e13_notclose(const double *__restrict__ a, const double *__restrict__ b, int n,
                                const int32_t *__restrict__ done, int32_t *__restrict__ notclose)
@@ -160,8 +195,11 @@ struct E13Work {
     double *seg = nullptr, *xsim = nullptr, *adj = nullptr, *sorted = nullptr, *keys = nullptr, *A = nullptr, *stds = nullptr;
     double2 *F = nullptr; int32_t *iota = nullptr, *perm = nullptr, *done = nullptr, *notclose = nullptr, *iters = nullptr, *n_active = nullptr;
     int *offsets = nullptr; void *cub_tmp = nullptr; size_t cub_bytes = 0;
+    float *key32 = nullptr, *key32_out = nullptr;
+    int cap_cnt = 0, cap_n = 0, offsets_n = 0;
     void release()
     {
+        cudaFree(key32); cudaFree(key32_out);
         cudaFree(seg); cudaFree(xsim); cudaFree(adj); cudaFree(sorted); cudaFree(keys); cudaFree(A); cudaFree(stds); cudaFree(F);
         cudaFree(iota); cudaFree(perm); cudaFree(done); cudaFree(notclose); cudaFree(iters); cudaFree(n_active); cudaFree(offsets);
         cudaFree(cub_tmp);
@@ -180,12 +218,23 @@ static int e13_sort_desc(E13Work &w, int cnt, int n, const double *keys_in, doub
                          int32_t *vals_out, cudaStream_t st)
 {
     if (n >= 32768) {
+        if (vals_in) {
+            const unsigned g = (unsigned)std::min<long long>(((long long)cnt * n + 255) / 256, 148 * 32);
+            k_e13_keys32<<<g, 256, 0, st>>>(keys_in, (size_t)cnt * n, w.key32);
+            for (int m = 0; m < cnt; ++m) {
+                size_t bytes = w.cub_bytes;
+                cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.key32 + (size_t)m * n, w.key32_out + (size_t)m * n,
+                                                                          vals_in + (size_t)m * n, vals_out + (size_t)m * n, n, 0, 32, st);
+                if (e != cudaSuccess) return mtg_cuda_check(e, "cub radix sort (32-bit keys)");
+                k_e13_fix_ties<<<(unsigned)std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(w.key32_out + (size_t)m * n, keys_in + (size_t)m * n, n,
+                                                                                            vals_out + (size_t)m * n);
+            }
+            mtg_count_launch((uint64_t)cnt * 5 + 1);
+            return mtg_cuda_check(cudaGetLastError(), "E13 rank order");
+        }
         for (int m = 0; m < cnt; ++m) {
             size_t bytes = w.cub_bytes;
-            cudaError_t e = vals_in
-                ? cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, keys_in + (size_t)m * n, keys_out + (size_t)m * n,
-                                                            vals_in + (size_t)m * n, vals_out + (size_t)m * n, n, 0, 64, st)
-                : cub::DeviceRadixSort::SortKeysDescending(w.cub_tmp, bytes, keys_in + (size_t)m * n, keys_out + (size_t)m * n, n, 0, 64, st);
+            cudaError_t e = cub::DeviceRadixSort::SortKeysDescending(w.cub_tmp, bytes, keys_in + (size_t)m * n, keys_out + (size_t)m * n, n, 0, 64, st);
             if (e != cudaSuccess) return mtg_cuda_check(e, "cub radix sort");
         }
         mtg_count_launch((uint64_t)cnt * 4);
@@ -256,22 +305,41 @@ static int e13_run_batch(Sim *s, std::map<long long, cufftHandle> &pz2d, std::ma
     return rc;
 }
 
-static int e13_work_alloc(E13Work &w, int cnt, int n)
+// workspace for batches of up to `cnt` series of up to `n` points; `use_cnt` x `use_n` is the batch about to run (the rows
+// of a batch are packed with stride use_n).  A cached workspace (one per simulator) is reused while it is large enough.
+static int e13_work_alloc(E13Work &w, int cnt, int n, int use_cnt = 0, int use_n = 0)
 {
+    if (use_n <= 0) { use_cnt = cnt; use_n = n; }
+    const bool big = use_n >= 32768;
+    if (use_cnt <= w.cap_cnt && use_n <= w.cap_n && (w.cap_n >= 32768) == big) {
+        if (!big && w.offsets_n != use_n) {
+            std::vector<int> off(w.cap_cnt + 1);
+            for (int m = 0; m <= w.cap_cnt; ++m) off[m] = m * use_n;
+            MTG_CUDA(cudaMemcpy(w.offsets, off.data(), sizeof(int) * (w.cap_cnt + 1), cudaMemcpyHostToDevice));
+            w.offsets_n = use_n;
+        }
+        return 0;
+    }
+    w.release();
+    w = E13Work();
+    if ((n >= 32768) != big) n = use_n;
+    if (cnt < use_cnt) cnt = use_cnt;
+    if (n < use_n) n = use_n;
     const size_t cn = (size_t)cnt * n, cm = (size_t)cnt * (n / 2 + 1);
     int rc = 0;
     if ((rc = e13_alloc((void **)&w.seg, cn * 8)) || (rc = e13_alloc((void **)&w.xsim, cn * 8)) || (rc = e13_alloc((void **)&w.adj, cn * 8)) ||
         (rc = e13_alloc((void **)&w.sorted, cn * 8)) || (rc = e13_alloc((void **)&w.keys, cn * 8)) || (rc = e13_alloc((void **)&w.A, cm * 8)) ||
         (rc = e13_alloc((void **)&w.F, cm * 16)) || (rc = e13_alloc((void **)&w.iota, cn * 4)) || (rc = e13_alloc((void **)&w.perm, cn * 4)) ||
+        (rc = e13_alloc((void **)&w.key32, big ? cn * 4 : 8)) || (rc = e13_alloc((void **)&w.key32_out, big ? cn * 4 : 8)) ||
         (rc = e13_alloc((void **)&w.stds, (size_t)cnt * 8)) || (rc = e13_alloc((void **)&w.done, (size_t)cnt * 4)) ||
         (rc = e13_alloc((void **)&w.notclose, (size_t)cnt * 4)) || (rc = e13_alloc((void **)&w.iters, (size_t)cnt * 4)) ||
         (rc = e13_alloc((void **)&w.n_active, 4)) || (rc = e13_alloc((void **)&w.offsets, (size_t)(cnt + 1) * sizeof(int)))) return rc;
     std::vector<int> off(cnt + 1);
-    for (int m = 0; m <= cnt; ++m) off[m] = m * n;
+    for (int m = 0; m <= cnt; ++m) off[m] = m * use_n;
     MTG_CUDA(cudaMemcpy(w.offsets, off.data(), sizeof(int) * (cnt + 1), cudaMemcpyHostToDevice));
     size_t b1 = 0, b2 = 0;
-    if (n >= 32768) {
-        cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, (double *)nullptr, (double *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, n);
+    if (big) {
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, (float *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, n);
         cub::DeviceRadixSort::SortKeysDescending(nullptr, b2, (double *)nullptr, (double *)nullptr, n);
     } else {
         cub::DeviceSegmentedSort::SortPairsDescending(nullptr, b1, (double *)nullptr, (double *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr,
@@ -279,44 +347,86 @@ static int e13_work_alloc(E13Work &w, int cnt, int n)
         cub::DeviceSegmentedSort::SortKeysDescending(nullptr, b2, (double *)nullptr, (double *)nullptr, (long long)cn, cnt, w.offsets, w.offsets + 1);
     }
     w.cub_bytes = b1 > b2 ? b1 : b2;
-    return e13_alloc(&w.cub_tmp, w.cub_bytes);
+    if ((rc = e13_alloc(&w.cub_tmp, w.cub_bytes))) return rc;
+    w.cap_cnt = cnt; w.cap_n = n; w.offsets_n = use_n;
+    return 0;
 }
 
-// E13 on the chunk held in s->d_lc: group the lightcurves by segment length and adjust each group
+void sim_e13_release(Sim *s)
+{
+    if (!s->e13_cache) return;
+    E13Work *w = (E13Work *)s->e13_cache;
+    w->release();
+    delete w;
+    s->e13_cache = nullptr;
+}
+
+// smallest 7-smooth integer >= v
+static int e13_next_smooth(int v)
+{
+    for (;; ++v) {
+        int r = v;
+        for (int f : {2, 3, 5, 7}) while (r % f == 0) r /= f;
+        if (r == 1) return v;
+    }
+}
+
+// E13 on the chunk held in s->d_lc.  Reference grid: the lightcurves are grouped by segment length (it varies by one
+// sample with the random shift) and each group is adjusted as a batch.  Lengthened grid (MTG_SIM_E13_PADDED): every
+// lightcurve is adjusted on a window of the same 7-smooth length starting at its segment, one batch, no host round trip.
 int sim_e13_chunk(Sim *s, int Lc, int l0, uint64_t seed, const double *d_pdf_variates, int32_t *d_iters, cudaStream_t stream)
 {
+    if (!s->e13_cache) s->e13_cache = new E13Work();
+    E13Work &w = *(E13Work *)s->e13_cache;
+    const double *var = d_pdf_variates ? d_pdf_variates + (size_t)l0 * s->cfg.n_fft : nullptr;      // injected variates: indexed by the GLOBAL lightcurve
+    const int max_iter = s->cfg.max_iter > 0 ? s->cfg.max_iter : 400;
+    if (s->cfg.flags & MTG_SIM_E13_PADDED) {
+        const int need = (int)ceil(s->cfg.sim_duration / s->cfg.sim_dt) + 2;
+        const int n = e13_next_smooth(need < 2 ? 2 : need);
+        if (n <= s->cfg.n_fft) {
+            int rc = e13_work_alloc(w, Lc, n);
+            if (rc) return rc;
+            const dim3 g2((unsigned)std::min<long long>((n + 255) / 256, 1024), Lc);
+            k_e13_gather<<<g2, 256, 0, stream>>>(s->d_lc, s->cfg.n_fft, s->d_seg, nullptr, n, s->cfg.mean, w.seg);
+            mtg_count_launch();
+            rc = e13_run_batch(s, s->plans, s->plans_d2z, w, Lc, n, s->cfg.pdf, s->cfg.mean, max_iter, var, (size_t)s->cfg.n_fft, nullptr, seed,
+                               (uint64_t)l0, stream);
+            if (rc) return rc;
+            k_e13_scatter_back<<<g2, 256, 0, stream>>>(s->d_lc, s->cfg.n_fft, s->d_seg, nullptr, n, w.xsim, w.iters, d_iters);
+            mtg_count_launch();
+            return mtg_cuda_check(cudaGetLastError(), "E13 (lengthened window)");
+        }
+    }
     std::vector<SegInfo> seg(Lc);
     MTG_CUDA(cudaMemcpyAsync(seg.data(), s->d_seg, sizeof(SegInfo) * Lc, cudaMemcpyDeviceToHost, stream));
     MTG_CUDA(cudaStreamSynchronize(stream));
     std::map<int, std::vector<int>> groups;
-    for (int l = 0; l < Lc; ++l) groups[seg[l].i1 - seg[l].i0].push_back(l);
+    int n_max = 0;
+    for (int l = 0; l < Lc; ++l) { const int n = seg[l].i1 - seg[l].i0; groups[n].push_back(l); n_max = std::max(n_max, n); }
+    int *d_members = nullptr;
+    int rc = e13_alloc((void **)&d_members, sizeof(int) * Lc);
     for (auto &kv : groups) {
+        if (rc) break;
         const int n = kv.first, cnt = (int)kv.second.size();
-        if (n < 2) { mtg_set_error("E13: segment of %d points", n); return MTG_EINVAL; }
-        E13Work w;
-        int rc = e13_work_alloc(w, cnt, n);
-        int *d_members = nullptr;
-        if (!rc) rc = e13_alloc((void **)&d_members, sizeof(int) * cnt);
+        if (n < 2) { mtg_set_error("E13: segment of %d points", n); rc = MTG_EINVAL; break; }
+        // one workspace for all groups of the chunk: sized for the longest segment and the whole chunk
+        rc = e13_work_alloc(w, Lc, (n >= 32768) == (n_max >= 32768) ? n_max : n, cnt, n);
         if (!rc) rc = mtg_cuda_check(cudaMemcpyAsync(d_members, kv.second.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, stream), "members");
         if (!rc) {
             const dim3 g2((unsigned)std::min<long long>((n + 255) / 256, 1024), cnt);
             k_e13_gather<<<g2, 256, 0, stream>>>(s->d_lc, s->cfg.n_fft, s->d_seg, d_members, n, s->cfg.mean, w.seg);
             mtg_count_launch();
-            // injected variates are indexed by the GLOBAL lightcurve: shift the base pointer by the chunk offset
-            const double *var = d_pdf_variates ? d_pdf_variates + (size_t)l0 * s->cfg.n_fft : nullptr;
-            rc = e13_run_batch(s, s->plans, s->plans_d2z, w, cnt, n, s->cfg.pdf, s->cfg.mean, s->cfg.max_iter > 0 ? s->cfg.max_iter : 400,
-                               var, (size_t)s->cfg.n_fft, d_members, seed, (uint64_t)l0, stream);
+            rc = e13_run_batch(s, s->plans, s->plans_d2z, w, cnt, n, s->cfg.pdf, s->cfg.mean, max_iter, var, (size_t)s->cfg.n_fft, d_members, seed,
+                               (uint64_t)l0, stream);
             if (!rc) {
                 k_e13_scatter_back<<<g2, 256, 0, stream>>>(s->d_lc, s->cfg.n_fft, s->d_seg, d_members, n, w.xsim, w.iters, d_iters);
                 mtg_count_launch();
-                rc = mtg_cuda_check(cudaStreamSynchronize(stream), "E13 group sync");
+                rc = mtg_cuda_check(cudaStreamSynchronize(stream), "E13 group sync");      // d_members is reused by the next group
             }
         }
-        cudaFree(d_members);
-        w.release();
-        if (rc) return rc;
     }
-    return 0;
+    cudaFree(d_members);
+    return rc;
 }
 
 extern "C" int mtg_e13_adjust_host(int n, const double *countrate, const double *xsim0, int max_iter,

@@ -475,6 +475,7 @@ extern "C" int mtg_sim_destroy(void *p)
     if (!parked) scratch_release(w);
     cudaFree(s->d_grid); cudaFree(s->d_lo); cudaFree(s->d_hi); cudaFree(s->d_exp); cudaFree(s->d_bkg); cudaFree(s->d_err);
     cudaFree(s->d_tw); cudaFree(s->d_qoff); cudaFree(s->d_flag); cudaFree(s->d_ampt);
+    sim_e13_release(s);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;

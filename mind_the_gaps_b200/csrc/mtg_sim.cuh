@@ -39,11 +39,13 @@ struct Sim {
     int capF = 0;                                             // lightcurves the fused chunk buffers hold
     double2 *d_Y = nullptr; int *d_mslot = nullptr, *d_cnt = nullptr; int *d_flag = nullptr;
     PsdCoef *d_coefF = nullptr; SegInfo *d_segF = nullptr; double *d_ampt = nullptr;
+    void *e13_cache = nullptr;                                // E13Work of mtg_e13.cu, kept between chunks
 };
 
 int sim_get_plan(Sim *s, std::map<long long, cufftHandle> &cache, cufftType type, int n, int batch, cufftHandle *out);
 // E13 PDF adjustment of the segments of the current chunk (in place in s->d_lc)
 int sim_e13_chunk(Sim *s, int Lc, int l0, uint64_t seed, const double *d_pdf_variates, int32_t *d_iters, cudaStream_t stream);
+void sim_e13_release(Sim *s);
 
 // ---- fused TK95 path (mtg_tk95.cu) --------------------------------------------------------------------
 // host: geometry for a grid / window (ok = 0 when the path does not apply), twiddle tables

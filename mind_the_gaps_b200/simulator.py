@@ -153,6 +153,7 @@ class Simulator(object):
         elif fft_length != "exact":
             raise ValueError("fft_length must be 'exact', 'fast' or an explicit length")
         self.fftndatapoints = len(self.sim_timestamps)
+        self._lengthened = fft_length != "exact"
         self.pdf = pdf
         self.max_iter = max_iter
         self.psd_model = psd_model
@@ -232,6 +233,7 @@ class Simulator(object):
             cfg.n_obs = n; cfg.n_fft = self.fftndatapoints; cfg.sim_dt = float(self.sim_dt)
             cfg.sim_duration = float(self.sim_duration); cfg.mean = float(self.mean)
             cfg.pdf = _PDF[self.pdf.lower()]; cfg.max_iter = int(self.max_iter)
+            cfg.flags = _native.SIM_E13_PADDED if self._lengthened else 0
             keep = [grid, lo, hi, ex]
             if isinstance(self.noise, GaussianNoise):
                 cfg.noise = _native.NOISE_GAUSSIAN; cfg.sigma_noise = float(self.noise.sigma_noise)

@@ -180,6 +180,48 @@ def test_e13_adjust_matches_oracle(n):
     assert np.mean(out == ref) > 0.995                               # identical ranks except FFT-rounding near-ties
 
 
+def test_e13_rank_order_with_colliding_float_keys():
+    """The rank order of an iteration comes from a radix sort on float(adj) plus a fix-up of runs of equal float keys by the
+    double values.  A series of unit variance on a level of 2e6 has a float resolution of 0.25: almost every key collides
+    (runs of thousands), and the result must still be the oracle's."""
+    n = 40000
+    rng = np.random.default_rng(5)
+    re, im = rng.normal(size=(2, n // 2 + 1))
+    lcr = osim.simulate_regular(n, 1.0, lambda w: oterms.psd_bendingpowerlaw(w, S0=4.0, omega0=0.05), 2.0e6, re, im)
+    draws = 2.0e6 + np.std(lcr) * rng.normal(size=n)
+    ref, its = osim.e13_adjust(lcr, draws, max_iter=50)
+    e13 = E13Simulator(2.0e6, "gaussian", max_iter=50)
+    lc = Lightcurve(np.arange(n, dtype=float), lcr, input_counts=False, dt=1.0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = e13.adjust_lightcurve_pdf(lc, None, max_iter=50, xsim=draws).countrate
+    assert np.array_equal(np.sort(out), np.sort(draws))
+    assert abs(e13.last_iterations - its) <= 1
+    assert np.mean(out == ref) > 0.99
+
+
+def test_e13_on_the_lengthened_grid_is_the_same_process():
+    """fft_length="fast" lets the PDF adjustment run on the segment lengthened to a 7-smooth length (MTG_SIM_E13_PADDED: one
+    batch per chunk, no Bluestein FFT).  The binned log-normal lightcurves must be the same process as on the reference's
+    grid: flux distribution, per-lightcurve mean / variance (two-sample KS), all positive, converged."""
+    import scipy.stats as sps
+    t, exposures = _gapped_setup(120, 9)
+    day = 86400.0
+    psd = BendingPowerlaw(S0=0.02, omega0=2 * np.pi / (20 * day))
+    out = {}
+    for mode, seed in (("exact", 3), ("fast", 4)):
+        simu = Simulator(psd, t, exposures, 0.5, pdf="Lognormal", extension_factor=2, aliasing_factor=2, max_iter=400, fft_length=mode)
+        rates, info = simu.generate_lightcurves(160, seed=seed, return_info=True)
+        assert np.all(rates > 0) and np.all(np.isfinite(rates))
+        assert np.all(info["e13_iterations"] < 400)
+        out[mode] = rates
+        simu.close()
+    assert sps.ks_2samp(out["exact"].ravel()[::7], out["fast"].ravel()[::7]).pvalue > 1e-3
+    for f in (lambda r: r.mean(axis=1), lambda r: r.var(axis=1)):
+        assert sps.ks_2samp(f(out["exact"]), f(out["fast"])).pvalue > 1e-3
+
+
 def test_e13_generate_lognormal_properties():
     t, exposures = _gapped_setup(50, 9)
     day = 86400.0

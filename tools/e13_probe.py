@@ -13,7 +13,8 @@ day = 86400.0
 tt_, exposures = window(N, 3)
 lc2 = GappyLightcurve(tt_, np.full(N, 0.01), np.full(N, 0.002), exposures, bkg_rate=np.full(N, 0.001), bkg_rate_err=np.full(N, 1e-4))
 psd2 = psd_models.BendingPowerlaw(S0=(0.3 * 0.01) ** 2, omega0=2 * np.pi / (20 * day))
-sim = lc2.get_simulator(psd2, "Lognormal", extension_factor=2, fft_length="fast", max_iter=400)
+mode = sys.argv[2] if len(sys.argv) > 2 else "fast"
+sim = lc2.get_simulator(psd2, "Lognormal", extension_factor=2, fft_length=mode, max_iter=400)
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     sim.generate_lightcurves(4, seed=1)
