@@ -108,8 +108,12 @@ __global__ void k_e13_phasor(double2 *__restrict__ F, const double *__restrict__
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         const double2 f = F[i];
-        const double r = hypot(f.x, f.y), a = A[i] * inv_n;
-        F[i] = r > 0.0 ? make_double2(a * (f.x / r), a * (f.y / r)) : make_double2(a, 0.0);
+        // A F/|F| with one reciprocal square root (1 ulp) instead of hypot and two divisions; |F|^2 of a sum of <= 2^22 flux
+        // values neither overflows nor underflows unless F is exactly 0 (angle(0) = 0)
+        const double r2 = fma(f.x, f.x, f.y * f.y), a = A[i] * inv_n;
+        const double sc = a * rsqrt(r2);
+        F[i] = (r2 > 0.0 && r2 < 1.0e300) ? make_double2(f.x * sc, f.y * sc)
+                                          : (r2 > 0.0 ? make_double2(a * (f.x / hypot(f.x, f.y)), a * (f.y / hypot(f.x, f.y))) : make_double2(a, 0.0));
     }
 }
 __global__ void k_e13_iota(int32_t *__restrict__ v, int n, int cnt)
@@ -352,8 +356,281 @@ static int e13_work_alloc(E13Work &w, int cnt, int n, int use_cnt = 0, int use_n
     return 0;
 }
 
+// ---- long series (n >= 32768): one lightcurve per slot ----------------------------------------------------------------
+// The batched loop above carries EVERY lightcurve of a batch through the FFT pair and the sort until the last one has
+// converged (max over the batch ~ 25 iterations where the mean is 19), and a batch of 1.3e6-point series streams every
+// array through HBM.  Long series therefore run one at a time: a slot (own stream, cuFFT plans and ~60 n bytes of work
+// arrays, which stay in the 126 MB L2 between the kernels of an iteration) carries ONE lightcurve to convergence, the
+// host reads its allclose flag after every iteration and hands the slot the next lightcurve as soon as it is done; two
+// slots keep the device busy while the host decides.  Accepting an iterate is a pointer swap, the rank matching and the
+// allclose test are one kernel, and the series moments come from a grid-wide reduction instead of one CTA per series.
+#define E13_NB 296
+struct E13Slot {
+    cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+    double *x[2] = {nullptr, nullptr};                 // current iterate / candidate (swapped on acceptance)
+    double *A = nullptr, *sorted = nullptr, *part = nullptr, *std_ = nullptr; double2 *F = nullptr;
+    float *k32 = nullptr, *k32o = nullptr; int32_t *perm = nullptr, *flag = nullptr, *h_flag = nullptr;
+    void *tmp = nullptr; size_t tmp_bytes = 0;
+    std::map<int, cufftHandle> fwd, inv;
+    int cap = 0;
+    int lc = -1, it = 0, n = 0, cur = 0;               // state: lightcurve in flight, iteration, length, index of the current iterate
+    double *dst = nullptr;
+    void free_buffers()
+    {
+        cudaFree(x[0]); cudaFree(x[1]); cudaFree(A); cudaFree(sorted); cudaFree(part); cudaFree(std_); cudaFree(F);
+        cudaFree(k32); cudaFree(k32o); cudaFree(perm); cudaFree(flag); cudaFree(tmp);
+        x[0] = x[1] = A = sorted = part = std_ = nullptr; F = nullptr; k32 = k32o = nullptr; perm = flag = nullptr; tmp = nullptr; cap = 0;
+    }
+    void release()
+    {
+        free_buffers();
+        for (auto &kv : fwd) cufftDestroy(kv.second);
+        for (auto &kv : inv) cufftDestroy(kv.second);
+        fwd.clear(); inv.clear();
+        if (h_flag) cudaFreeHost(h_flag);
+        if (ev) cudaEventDestroy(ev);
+        if (st) cudaStreamDestroy(st);
+        h_flag = nullptr; ev = nullptr; st = nullptr;
+    }
+};
+struct E13Large {
+    std::vector<E13Slot> slots; int32_t *iota = nullptr; int iota_n = 0; cudaEvent_t ev_in = nullptr;
+    int32_t *h_iters = nullptr; int h_iters_n = 0;
+    void release()
+    {
+        for (auto &q : slots) q.release();
+        slots.clear();
+        cudaFree(iota); iota = nullptr; iota_n = 0;
+        if (h_iters) cudaFreeHost(h_iters);
+        h_iters = nullptr; h_iters_n = 0;
+        if (ev_in) cudaEventDestroy(ev_in);
+        ev_in = nullptr;
+    }
+};
+
+__global__ void k_e13_addmean(const double *__restrict__ src, int n, double mean, double *__restrict__ dst)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i] + mean;
+}
+// partial sums of d = x - x[0] and d^2 per block; k_e13_moments_fin turns them into the population standard deviation
+__global__ void __launch_bounds__(256) k_e13_moments(const double *__restrict__ x, int n, double *__restrict__ part)
+{
+    __shared__ double sh[2][8];
+    const double shift = x[0];
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) { const double d = x[i] - shift; s1 += d; s2 = fma(d, d, s2); }
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+}
+__global__ void k_e13_moments_fin(const double *__restrict__ part, int nb, int n, double *__restrict__ out_std)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nb; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+    const double m = a / n, v = b / n - m * m;
+    out_std[0] = sqrt(v > 0.0 ? v : 0.0);
+}
+// out[perm[r]] = sorted_desc[r] and the np.allclose(out, xold, rtol=1e-4, atol=1e-8) test of the same elements
+__global__ void __launch_bounds__(256) k_e13_match_check(const int32_t *__restrict__ perm, const double *__restrict__ sorted_desc,
+                                                         const double *__restrict__ xold, double *__restrict__ out, int n,
+                                                         int32_t *__restrict__ flag)
+{
+    int bad = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const int i = perm[r];
+        const double v = sorted_desc[r], y = xold[i];
+        out[i] = v;
+        if (!(fabs(v - y) <= 1e-8 + 1e-4 * fabs(y))) bad = 1;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;
+}
+
+static int e13_slot_reserve(E13Slot &q, int n)
+{
+    if (!q.st) {
+        MTG_CUDA(cudaStreamCreateWithFlags(&q.st, cudaStreamNonBlocking));
+        MTG_CUDA(cudaEventCreateWithFlags(&q.ev, cudaEventDisableTiming));
+        MTG_CUDA(cudaMallocHost((void **)&q.h_flag, sizeof(int32_t)));
+    }
+    if (n <= q.cap) return 0;
+    q.free_buffers();
+    const size_t N = (size_t)n, Mh = N / 2 + 1;
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, (float *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, n);
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, b2, (double *)nullptr, (double *)nullptr, n);
+    q.tmp_bytes = b1 > b2 ? b1 : b2;
+    int rc = 0;
+    if ((rc = e13_alloc((void **)&q.x[0], N * 8)) || (rc = e13_alloc((void **)&q.x[1], N * 8)) || (rc = e13_alloc((void **)&q.A, Mh * 8)) ||
+        (rc = e13_alloc((void **)&q.sorted, N * 8)) || (rc = e13_alloc((void **)&q.F, Mh * 16)) || (rc = e13_alloc((void **)&q.k32, N * 4)) ||
+        (rc = e13_alloc((void **)&q.k32o, N * 4)) || (rc = e13_alloc((void **)&q.perm, N * 4)) || (rc = e13_alloc((void **)&q.flag, 4)) ||
+        (rc = e13_alloc((void **)&q.part, sizeof(double) * 2 * E13_NB)) || (rc = e13_alloc((void **)&q.std_, 8)) ||
+        (rc = e13_alloc(&q.tmp, q.tmp_bytes))) return rc;
+    q.cap = n;
+    return 0;
+}
+
+static int e13_slot_plan(E13Slot &q, int n, bool forward, cufftHandle *out)
+{
+    std::map<int, cufftHandle> &cache = forward ? q.fwd : q.inv;
+    auto it = cache.find(n);
+    if (it != cache.end()) { *out = it->second; return 0; }
+    cufftHandle h;
+    cufftResult r = cufftPlan1d(&h, n, forward ? CUFFT_D2Z : CUFFT_Z2D, 1);
+    if (r != CUFFT_SUCCESS) { mtg_set_error("cufftPlan1d(n=%d) failed: %d", n, (int)r); return MTG_ENOMEM; }
+    cufftSetStream(h, q.st);
+    cache[n] = h; *out = h;
+    return 0;
+}
+
+// enqueue the set-up of one lightcurve on slot q: q.x[1] holds the TK95 segment (mean included) when src == nullptr
+static int e13_slot_begin(E13Slot &q, const double *src, int n, double mean, int pdf, const double *variates, uint64_t seed, uint64_t lc_global,
+                          bool draws_ready)
+{
+    int rc;
+    cufftHandle fwd;
+    if ((rc = e13_slot_plan(q, n, true, &fwd))) return rc;
+    const unsigned g = (unsigned)std::min((n + 255) / 256, 148 * 8);
+    const int Mh = n / 2 + 1;
+    if (src) k_e13_addmean<<<g, 256, 0, q.st>>>(src, n, mean, q.x[1]);
+    if (!draws_ready) {
+        k_e13_moments<<<E13_NB, 256, 0, q.st>>>(q.x[1], n, q.part);
+        k_e13_moments_fin<<<1, 32, 0, q.st>>>(q.part, E13_NB, n, q.std_);
+        k_e13_draw<<<dim3(g, 1), 256, 0, q.st>>>(pdf, mean, q.std_, n, variates, 0, nullptr, seed, lc_global, q.x[0]);
+    }
+    if (cufftExecD2Z(fwd, q.x[1], (cufftDoubleComplex *)q.F) != CUFFT_SUCCESS) { mtg_set_error("cufftExecD2Z failed"); return MTG_EINVAL; }
+    k_e13_amplitude<<<g, 256, 0, q.st>>>(q.F, (size_t)Mh, 1.0 / (double)(n / 2 + 1), q.A);
+    size_t bytes = q.tmp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortKeysDescending(q.tmp, bytes, q.x[0], q.sorted, n, 0, 64, q.st);
+    if (e != cudaSuccess) return mtg_cuda_check(e, "cub radix sort");
+    mtg_count_launch(16);
+    q.n = n; q.it = 0; q.cur = 0;
+    return mtg_cuda_check(cudaGetLastError(), "E13 set-up");
+}
+
+// enqueue one iteration on slot q; its allclose flag lands in q.h_flag when q.ev completes
+static int e13_slot_iterate(E13Slot &q, const int32_t *iota)
+{
+    int rc;
+    const int n = q.n, Mh = n / 2 + 1;
+    cufftHandle fwd, inv;
+    if ((rc = e13_slot_plan(q, n, true, &fwd)) || (rc = e13_slot_plan(q, n, false, &inv))) return rc;
+    const unsigned g = (unsigned)std::min((n + 255) / 256, 148 * 8);
+    double *x = q.x[q.cur], *adj = q.x[q.cur ^ 1];
+    if (cufftExecD2Z(fwd, x, (cufftDoubleComplex *)q.F) != CUFFT_SUCCESS) { mtg_set_error("cufftExecD2Z failed"); return MTG_EINVAL; }
+    k_e13_phasor<<<g, 256, 0, q.st>>>(q.F, q.A, (size_t)Mh, 1.0 / (double)n);
+    if (cufftExecZ2D(inv, (cufftDoubleComplex *)q.F, adj) != CUFFT_SUCCESS) { mtg_set_error("cufftExecZ2D failed"); return MTG_EINVAL; }
+    k_e13_keys32<<<g, 256, 0, q.st>>>(adj, (size_t)n, q.k32);
+    size_t bytes = q.tmp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(q.tmp, bytes, q.k32, q.k32o, iota, q.perm, n, 0, 32, q.st);
+    if (e != cudaSuccess) return mtg_cuda_check(e, "cub radix sort (32-bit keys)");
+    k_e13_fix_ties<<<g, 256, 0, q.st>>>(q.k32o, adj, n, q.perm);
+    cudaMemsetAsync(q.flag, 0, sizeof(int32_t), q.st);
+    k_e13_match_check<<<g, 256, 0, q.st>>>(q.perm, q.sorted, x, adj, n, q.flag);
+    cudaMemcpyAsync(q.h_flag, q.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, q.st);
+    cudaEventRecord(q.ev, q.st);
+    mtg_count_launch(20);
+    return mtg_cuda_check(cudaGetLastError(), "E13 iteration");
+}
+
+static int e13_slots()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MTG_E13_SLOTS"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > 8) v = 8; }
+    return v;
+}
+
+static int e13_large_prepare(E13Large &g, int n_max, int count)
+{
+    if ((int)g.slots.size() != e13_slots()) { g.release(); g.slots.resize(e13_slots()); }
+    if (!g.ev_in) MTG_CUDA(cudaEventCreateWithFlags(&g.ev_in, cudaEventDisableTiming));
+    if (g.iota_n < n_max) {
+        cudaFree(g.iota); g.iota = nullptr; g.iota_n = 0;
+        int rc = e13_alloc((void **)&g.iota, sizeof(int32_t) * (size_t)n_max);
+        if (rc) return rc;
+        k_e13_iota<<<148 * 8, 256>>>(g.iota, n_max, 1);
+        MTG_CUDA(cudaDeviceSynchronize());
+        g.iota_n = n_max;
+    }
+    if (g.h_iters_n < count) {
+        if (g.h_iters) cudaFreeHost(g.h_iters);
+        g.h_iters = nullptr; g.h_iters_n = 0;
+        MTG_CUDA(cudaMallocHost((void **)&g.h_iters, sizeof(int32_t) * (size_t)count));
+        g.h_iters_n = count;
+    }
+    const int used = std::min<int>((int)g.slots.size(), count);
+    for (int k = 0; k < used; ++k) { int rc = e13_slot_reserve(g.slots[k], n_max); if (rc) return rc; }
+    return 0;
+}
+
+// Adjust `count` long series.  Series k: `n[k]` points at src[k] (device; the TK95 segment WITHOUT the mean), result written to
+// dst[k] (may alias src[k]); `stream` orders the inputs before and the results after.  draws0: injected initial draws (device,
+// one series, mean already in src) -- the test entry.
+static int e13_run_large(E13Large &g, int count, const int *n, double *const *src, double *const *dst, double mean, int pdf, int max_iter,
+                         const double *const *variates, uint64_t seed, uint64_t lc_offset, int32_t *d_iters, cudaStream_t stream,
+                         const double *draws0 = nullptr)
+{
+    int n_max = 0;
+    for (int k = 0; k < count; ++k) n_max = std::max(n_max, n[k]);
+    int rc = e13_large_prepare(g, n_max, count);
+    if (rc) return rc;
+    MTG_CUDA(cudaEventRecord(g.ev_in, stream));
+    const int used = std::min<int>((int)g.slots.size(), count);
+    int next = 0, active = 0;
+    auto start = [&](E13Slot &q) -> int {
+        const int k = next++;
+        q.lc = k; q.dst = dst[k];
+        int r;
+        if (draws0) {
+            MTG_CUDA(cudaMemcpyAsync(q.x[0], draws0, sizeof(double) * n[k], cudaMemcpyDeviceToDevice, q.st));
+            MTG_CUDA(cudaMemcpyAsync(q.x[1], src[k], sizeof(double) * n[k], cudaMemcpyDeviceToDevice, q.st));
+            r = e13_slot_begin(q, nullptr, n[k], mean, pdf, nullptr, seed, lc_offset + k, true);
+        } else r = e13_slot_begin(q, src[k], n[k], mean, pdf, variates ? variates[k] : nullptr, seed, lc_offset + k, false);
+        if (!r) r = e13_slot_iterate(q, g.iota);
+        if (!r) ++active;
+        return r;
+    };
+    for (int k = 0; k < used && !rc; ++k) {
+        g.slots[k].lc = -1;
+        MTG_CUDA(cudaStreamWaitEvent(g.slots[k].st, g.ev_in, 0));
+        rc = start(g.slots[k]);
+    }
+    while (active > 0 && !rc) {
+        for (int k = 0; k < used && !rc; ++k) {
+            E13Slot &q = g.slots[k];
+            if (q.lc < 0) continue;
+            if ((rc = mtg_cuda_check(cudaEventSynchronize(q.ev), "E13 iteration"))) break;
+            const bool notclose = *q.h_flag != 0;
+            if (notclose && q.it < max_iter) { q.cur ^= 1; q.it += 1; rc = e13_slot_iterate(q, g.iota); continue; }
+            // converged (or out of iterations): the result is the CURRENT iterate, not the candidate (simulator.py:129)
+            MTG_CUDA(cudaMemcpyAsync(q.dst, q.x[q.cur], sizeof(double) * q.n, cudaMemcpyDeviceToDevice, q.st));
+            g.h_iters[q.lc] = q.it;
+            q.lc = -1; --active;
+            if (next < count) rc = start(q);
+        }
+    }
+    for (int k = 0; k < used; ++k) {
+        cudaEventRecord(g.slots[k].ev, g.slots[k].st);
+        cudaStreamWaitEvent(stream, g.slots[k].ev, 0);
+    }
+    if (!rc && d_iters) rc = mtg_cuda_check(cudaMemcpyAsync(d_iters, g.h_iters, sizeof(int32_t) * count, cudaMemcpyHostToDevice, stream), "E13 iterations");
+    if (rc) cudaDeviceSynchronize();
+    return rc;
+}
+
 void sim_e13_release(Sim *s)
 {
+    if (s->e13_large) {
+        E13Large *g = (E13Large *)s->e13_large;
+        g->release();
+        delete g;
+        s->e13_large = nullptr;
+    }
     if (!s->e13_cache) return;
     E13Work *w = (E13Work *)s->e13_cache;
     w->release();
@@ -376,14 +653,41 @@ static int e13_next_smooth(int v)
 // lightcurve is adjusted on a window of the same 7-smooth length starting at its segment, one batch, no host round trip.
 int sim_e13_chunk(Sim *s, int Lc, int l0, uint64_t seed, const double *d_pdf_variates, int32_t *d_iters, cudaStream_t stream)
 {
-    if (!s->e13_cache) s->e13_cache = new E13Work();
-    E13Work &w = *(E13Work *)s->e13_cache;
     const double *var = d_pdf_variates ? d_pdf_variates + (size_t)l0 * s->cfg.n_fft : nullptr;      // injected variates: indexed by the GLOBAL lightcurve
     const int max_iter = s->cfg.max_iter > 0 ? s->cfg.max_iter : 400;
+    int n_pad = 0;
     if (s->cfg.flags & MTG_SIM_E13_PADDED) {
         const int need = (int)ceil(s->cfg.sim_duration / s->cfg.sim_dt) + 2;
-        const int n = e13_next_smooth(need < 2 ? 2 : need);
-        if (n <= s->cfg.n_fft) {
+        n_pad = e13_next_smooth(need < 2 ? 2 : need);
+        if (n_pad > s->cfg.n_fft) n_pad = 0;
+    }
+    if (n_pad >= 32768 || (!n_pad && s->cfg.sim_duration / s->cfg.sim_dt >= 32770.0)) {
+        // long series: one lightcurve per slot (e13_run_large)
+        std::vector<SegInfo> seg(Lc);
+        MTG_CUDA(cudaMemcpyAsync(seg.data(), s->d_seg, sizeof(SegInfo) * Lc, cudaMemcpyDeviceToHost, stream));
+        MTG_CUDA(cudaStreamSynchronize(stream));
+        std::vector<int> nn(Lc);
+        std::vector<double *> ptr(Lc);
+        std::vector<const double *> vptr(Lc);
+        bool all_long = true;
+        for (int l = 0; l < Lc; ++l) {
+            const int n = n_pad ? n_pad : seg[l].i1 - seg[l].i0;
+            const int start = n_pad ? (seg[l].i0 + n <= s->cfg.n_fft ? seg[l].i0 : s->cfg.n_fft - n) : seg[l].i0;
+            nn[l] = n; ptr[l] = s->d_lc + (size_t)l * s->cfg.n_fft + start;
+            vptr[l] = var ? var + (size_t)l * s->cfg.n_fft : nullptr;
+            if (n < 32768) all_long = false;
+        }
+        if (all_long) {
+            if (!s->e13_large) s->e13_large = new E13Large();
+            return e13_run_large(*(E13Large *)s->e13_large, Lc, nn.data(), ptr.data(), ptr.data(), s->cfg.mean, s->cfg.pdf, max_iter,
+                                 var ? vptr.data() : nullptr, seed, (uint64_t)l0, d_iters, stream);
+        }
+    }
+    if (!s->e13_cache) s->e13_cache = new E13Work();
+    E13Work &w = *(E13Work *)s->e13_cache;
+    if (n_pad) {
+        const int n = n_pad;
+        {
             int rc = e13_work_alloc(w, Lc, n);
             if (rc) return rc;
             const dim3 g2((unsigned)std::min<long long>((n + 255) / 256, 1024), Lc);
@@ -433,6 +737,23 @@ extern "C" int mtg_e13_adjust_host(int n, const double *countrate, const double 
                                    double *out_x, int32_t *out_iters)
 {
     if (n < 2 || !countrate || !xsim0 || !out_x || max_iter < 0) { mtg_set_error("mtg_e13_adjust_host: bad argument"); return MTG_EINVAL; }
+    if (n >= 32768) {              // the long-series path (one slot)
+        E13Large g;
+        double *d_in = nullptr, *d_x0 = nullptr; int32_t *d_it = nullptr;
+        int rc = e13_alloc((void **)&d_in, sizeof(double) * n);
+        if (!rc) rc = e13_alloc((void **)&d_x0, sizeof(double) * n);
+        if (!rc) rc = e13_alloc((void **)&d_it, sizeof(int32_t));
+        if (!rc) rc = mtg_cuda_check(cudaMemcpy(d_in, countrate, sizeof(double) * n, cudaMemcpyHostToDevice), "h2d");
+        if (!rc) rc = mtg_cuda_check(cudaMemcpy(d_x0, xsim0, sizeof(double) * n, cudaMemcpyHostToDevice), "h2d");
+        double *srcs[1] = {d_in};
+        if (!rc) rc = e13_run_large(g, 1, &n, srcs, srcs, 0.0, MTG_PDF_UNIFORM, max_iter, nullptr, 0, 0, d_it, (cudaStream_t)0, d_x0);
+        if (!rc) rc = mtg_cuda_check(cudaDeviceSynchronize(), "E13");
+        if (!rc) rc = mtg_cuda_check(cudaMemcpy(out_x, d_in, sizeof(double) * n, cudaMemcpyDeviceToHost), "d2h");
+        if (!rc && out_iters) rc = mtg_cuda_check(cudaMemcpy(out_iters, d_it, sizeof(int32_t), cudaMemcpyDeviceToHost), "d2h");
+        cudaFree(d_in); cudaFree(d_x0); cudaFree(d_it);
+        g.release();
+        return rc;
+    }
     Sim tmp;                      // only used as a cuFFT plan cache
     E13Work w;
     int rc = e13_work_alloc(w, 1, n);

@@ -40,6 +40,7 @@ struct Sim {
     double2 *d_Y = nullptr; int *d_mslot = nullptr, *d_cnt = nullptr; int *d_flag = nullptr;
     PsdCoef *d_coefF = nullptr; SegInfo *d_segF = nullptr; double *d_ampt = nullptr;
     void *e13_cache = nullptr;                                // E13Work of mtg_e13.cu, kept between chunks
+    void *e13_large = nullptr;                                // E13Large of mtg_e13.cu (slots of the long-series path)
 };
 
 int sim_get_plan(Sim *s, std::map<long long, cufftHandle> &cache, cufftType type, int n, int batch, cufftHandle *out);
