@@ -502,7 +502,9 @@ static int sim_chunk(const Sim *s, int L)
     size_t budget = (size_t)12 << 30;
     if (const char *e = getenv("MTG_SIM_MB")) { long v = atol(e); if (v > 0) budget = (size_t)v << 20; }
     size_t per = (size_t)s->M * 16 + (size_t)s->cfg.n_fft * 8;
-    if (s->cfg.pdf != MTG_PDF_GAUSSIAN) per += (size_t)s->cfg.n_fft * 8 * 8;      // E13 work arrays
+    // E13 work arrays: per lightcurve of the chunk on the batched path (short series); long series run in a fixed number of
+    // slots (mtg_e13.cu, e13_run_large), whatever the chunk
+    if (s->cfg.pdf != MTG_PDF_GAUSSIAN && s->cfg.sim_duration / s->cfg.sim_dt < 32770.0) per += (size_t)s->cfg.n_fft * 8 * 8;
     size_t n = budget / per / 2;                                                  // leave room for cuFFT work areas
     if (n < 1) n = 1;
     return (int)(n < (size_t)L ? n : (size_t)L);

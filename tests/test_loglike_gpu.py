@@ -266,3 +266,40 @@ def test_c5_real_shape_parity_at_size():
     ll_s = gp_s.log_likelihood_batch(y[:n], p[:6])
     ref_d = ogp.loglike_params(spec, p[:6], t[:n], y[:n], dy[:n], mean=float(np.mean(y)), dense=True)
     np.testing.assert_allclose(ll_s, ref_d, rtol=1e-9)
+
+
+def test_host_entries_on_two_devices_from_one_process():
+    """VERDICT r1 (10) / ADVICE r1: the host entries keep one context (streams, pinned staging, device buffers) PER DEVICE.
+    One process drives device 0, then device 1, then device 0 again through mtg_loglike_host / mtg_loglike_grad_host: every
+    call must give the same (oracle-checked) numbers, also at a batch large enough for the chunk pipeline.  Runs when at
+    least two GPUs are visible (`gpurun --gpus 2`); the single-GPU suite skips it."""
+    lib = _native.lib()
+    if lib.mtg_device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    N = 64
+    t, y, dy, _ = fake_lightcurve(N, 5)
+    kernel, spec = build("drw+lor")
+    model = GP(kernel, mean=0.0).device_model()
+    rng = np.random.default_rng(3)
+    diag = np.ascontiguousarray((dy + 1e-12) ** 2); yy = np.ascontiguousarray(y - y.mean()); tt = np.ascontiguousarray(t)
+    out = {}
+    try:
+        for B in (300, 2 * 2 * 148 * 512 + 77):
+            p = np.ascontiguousarray(c2_truth()[None, :] + rng.normal(0, 0.1, (B, 5)))
+            for visit, dev in enumerate((0, 1, 0)):
+                _native.check(lib.mtg_set_device(dev))
+                ll = np.empty(B); ll2 = np.empty(B); g = np.empty((B, 5)); st = np.empty(B, dtype=np.int32)
+                _native.check(lib.mtg_loglike_host(ctypes.byref(model), N, 1, B, B, _native.ptr(tt), _native.ptr(yy), _native.ptr(diag), None,
+                                                   _native.ptr(p), _native.ptr(ll), _native.ptr(st), 0))
+                _native.check(lib.mtg_loglike_grad_host(ctypes.byref(model), N, 1, B, B, _native.ptr(tt), _native.ptr(yy), _native.ptr(diag), None,
+                                                        _native.ptr(p), _native.ptr(ll2), _native.ptr(g), _native.ptr(st), 0))
+                assert np.all(st == 0)
+                out[(B, visit)] = (ll, g)
+            for visit in (1, 2):
+                np.testing.assert_array_equal(out[(B, visit)][0], out[(B, 0)][0])
+                np.testing.assert_array_equal(out[(B, visit)][1], out[(B, 0)][1])
+            idx = rng.choice(B, 32, replace=False)
+            ref = ogp.loglike_params(spec, p[idx], t, y - y.mean(), dy)
+            np.testing.assert_allclose(out[(B, 1)][0][idx], ref, rtol=RTOL)
+    finally:
+        lib.mtg_set_device(0)

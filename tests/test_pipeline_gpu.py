@@ -76,6 +76,40 @@ def test_gpmodelling_fit_and_posteriors_c1():
     assert abs(np.mean([l.mean for l in lcs]) - lc.mean) < 0.1
 
 
+def test_generate_from_posteriors_uses_each_drawn_sample():
+    """a9 (gpmodelling.py:478-539): every simulated lightcurve is generated from ITS OWN posterior sample.  Two tight clusters
+    of posterior samples whose variances differ by e^2 and bend frequencies by e^2: refitting the simulated lightcurves
+    (batched device L-BFGS) must recover, cluster by cluster, the parameters each lightcurve was drawn with, and the
+    lightcurves must carry the data's window, mean and a positive error column."""
+    from mind_the_gaps_b200 import fitting
+    lc, truth = make_lc(400, 7)
+    bounds = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
+    gpm = GPModelling(lc, DampedRandomWalk(truth[0], truth[1], bounds=bounds))
+    rng = np.random.default_rng(1)
+    centres = np.array([[truth[0] + 1.0, truth[1] + 1.0], [truth[0] - 1.0, truth[1] - 1.0]])
+    samples = np.concatenate([c + rng.normal(0, 0.01, (50, 2)) for c in centres])
+    gpm._mcmc_samples = samples
+    gpm._loglikelihoods = np.zeros(len(samples))
+    nsims = 300
+    np.random.seed(12)
+    idx = np.random.randint(len(samples), size=nsims)            # the draw generate_from_posteriors makes first
+    np.random.seed(12)
+    lcs = gpm.generate_from_posteriors(nsims=nsims)
+    assert len(lcs) == nsims
+    Y = np.array([l.y for l in lcs]); DY = np.array([l.dy for l in lcs])
+    assert all(np.array_equal(l.times, lc.times) for l in lcs[:5]) and np.all(DY > 0) and np.all(np.isfinite(Y))
+    assert abs(Y.mean() - lc.mean) < 0.02 * lc.mean
+    res = fitting.fit_lightcurves(gpm.gp, lc.times, Y, DY, x0=samples[idx])
+    xhat = np.array([r.x for r in res])
+    for k, c in enumerate(centres):
+        sel = idx // 50 == k
+        assert sel.sum() > 100
+        med = np.median(xhat[sel], axis=0)
+        assert np.all(np.abs(med - c) < 0.35), (k, med, c)
+    # the two clusters are told apart lightcurve by lightcurve in variance (2 in log) for the large majority
+    assert np.mean((xhat[:, 0] > truth[0]) == (idx // 50 == 0)) > 0.9
+
+
 def test_lrt_driver_null_distribution():
     lc, truth = make_lc(200, 4)
     b_drw = dict(log_S0=(-15, 5), log_omega0=(-20, -5))
