@@ -180,6 +180,29 @@ def test_e13_adjust_matches_oracle(n):
     assert np.mean(out == ref) > 0.995                               # identical ranks except FFT-rounding near-ties
 
 
+@pytest.mark.parametrize("n", [3000, 40000])
+def test_e13_stops_at_max_iter_with_the_last_accepted_iterate(n):
+    """simulator.py:111-129: the loop ends after max_iter iterations even if not converged, and the result is the last
+    ACCEPTED iterate (xsim, not xsim_adjust); both the batched (short series) and the per-slot (long series) loop."""
+    rng = np.random.default_rng(n + 1)
+    re, im = rng.normal(size=(2, n // 2 + 1))
+    lcr = osim.simulate_regular(n, 1.0, lambda w: oterms.psd_bendingpowerlaw(w, S0=4.0, omega0=0.05), 10.0, re, im)
+    s, scale = osim.create_log_normal_params(10.0, np.std(lcr))
+    draws = scale * np.exp(s * rng.normal(size=n))
+    import warnings
+    for max_iter in (0, 3):
+        ref, its = osim.e13_adjust(lcr, draws, max_iter=max_iter)
+        assert its == max_iter
+        e13 = E13Simulator(10.0, "lognormal", max_iter=max_iter)
+        lc = Lightcurve(np.arange(n, dtype=float), lcr.copy(), input_counts=False, dt=1.0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = e13.adjust_lightcurve_pdf(lc, None, max_iter=max_iter, xsim=draws).countrate
+        assert e13.last_iterations == max_iter
+        assert np.array_equal(np.sort(out), np.sort(draws))
+        assert np.mean(out == ref) > (0.999 if max_iter == 0 else 0.995)
+
+
 def test_e13_rank_order_with_colliding_float_keys():
     """The rank order of an iteration comes from a radix sort on float(adj) plus a fix-up of runs of equal float keys by the
     double values.  A series of unit variance on a level of 2e6 has a float resolution of 0.25: almost every key collides
