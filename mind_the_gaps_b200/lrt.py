@@ -176,7 +176,7 @@ def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
 def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
                      extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
                      max_iter=200, device=None, distributed=None, chunk=None, pipeline=3, return_lightcurves=False,
-                     simulator_kwargs=None, refine_walkers=0, refine_steps=0):
+                     simulator_kwargs=None, refine_walkers=0, refine_steps=0, refine_block=25):
     """Simulate one lightcurve per row of ``null_samples`` (posterior draws of the null kernel's
     parameters) on the window of ``lightcurve`` and MLE-fit each with both kernels.
 
@@ -195,8 +195,9 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     ``refine_walkers, refine_steps``: when both are positive every fit is followed, as in the reference's notebook
     (``GPModelling(lc, kernel).derive_posteriors(fit=True, walkers=30, max_steps=500)`` then ``max_loglikelihood``,
     tutorial_ppp.ipynb cells 11-13), by a short stretch-move chain started in a 10 % Gaussian ball around the optimum
-    (``spread_walkers``) -- all simulations in lock step in ONE launch of the device ensemble sampler (kernel K8) --
-    and the largest log-likelihood visited replaces the optimiser's.  Returns an ``LRTResult`` holding the arrays for ALL simulations (gathered
+    (``spread_walkers``) -- all simulations of a chunk in lock step in the device ensemble sampler (kernel K8), the run cut
+    into launches of ``refine_block`` steps (the same chain however it is cut) -- and the largest log-likelihood visited
+    replaces the optimiser's.  Returns an ``LRTResult`` holding the arrays for ALL simulations (gathered
     over ranks when ``torch.distributed`` is initialised)."""
     import concurrent.futures
     import torch
@@ -273,9 +274,18 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
         pos = torch.from_numpy(np.ascontiguousarray(p0)).to(device)
         lpw = torch.empty((Lc, W), dtype=torch.float64, device=device)
         blp = torch.empty(Lc, dtype=torch.float64, device=device); bpos = torch.empty((Lc, nd), dtype=torch.float64, device=device)
-        _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N, Lc, Lc, W, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(), means.data_ptr(),
-                                           pos.data_ptr(), lpw.data_ptr(), 1, int(refine_steps), 2.0, ens_seed, 0,
-                                           None, None, None, blp.data_ptr(), bpos.data_ptr(), _native.FLAG_DS_MEAN, sp))
+        # The run is cut into launches of `refine_block` steps (same chain: the Philox counters carry the absolute step, the
+        # best-so-far state continues across launches).  One launch of all the steps keeps a CTA alive for the whole run, so
+        # a shard of slightly more ensembles than the device holds at once (2 x 2368 at 30 walkers) pays a second full
+        # wave for the remainder; short launches from the pipeline's streams let the block scheduler pack the remainder
+        # beside the other chunks' work instead.
+        done = 0
+        while done < int(refine_steps):
+            n_st = min(int(refine_block), int(refine_steps) - done)
+            _native.check(lib.mtg_ensemble_dev(ctypes.byref(model), N, Lc, Lc, W, t_dev.data_ptr(), y.data_ptr(), diag.data_ptr(), means.data_ptr(),
+                                               pos.data_ptr(), lpw.data_ptr(), 1 if done == 0 else 0, n_st, 2.0, ens_seed, done,
+                                               None, None, None, blp.data_ptr(), bpos.data_ptr(), _native.FLAG_DS_MEAN, sp))
+            done += n_st
         b = blp.cpu().numpy(); bp = bpos.cpu().numpy()
         better = b > f_best
         return np.where(better, b, f_best), np.where(better[:, None], bp, x_best)

@@ -18,6 +18,7 @@ chunk = int(sys.argv[3]) if len(sys.argv) > 3 and int(sys.argv[3]) > 0 else None
 pipeline = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 rw = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 rs = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+rb = int(sys.argv[7]) if len(sys.argv) > 7 else 25
 N = 1000
 tt, exposures = window(N, 2)
 lc = GappyLightcurve(tt, np.full(N, 0.5), np.full(N, 0.02), exposures)
@@ -31,7 +32,7 @@ lib = _native.lib()
 for rep in range(2):
     l0 = lib.mtg_launch_count()
     t0 = time.perf_counter()
-    res = lrt.simulate_and_fit(lc, null_k, alt_k, samples, n_starts_null=2, n_starts_alt=8, seed=3, distributed=False, chunk=chunk, pipeline=pipeline, refine_walkers=rw, refine_steps=rs,
+    res = lrt.simulate_and_fit(lc, null_k, alt_k, samples, n_starts_null=2, n_starts_alt=8, seed=3, distributed=False, chunk=chunk, pipeline=pipeline, refine_walkers=rw, refine_steps=rs, refine_block=rb,
                                simulator_kwargs={"fft_length": mode})
     wall = time.perf_counter() - t0
     print("rep %d: %d sims  wall %.3f s  %.0f sims/s  launches %d  timings %s  T median %.3f p95 %.3f  status_alt %s" % (
