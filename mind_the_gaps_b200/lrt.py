@@ -183,10 +183,9 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     ``null_slots``: positions in the alternative's parameter vector of the parameters it shares with the
     null model (default: the trailing ``len(null)`` ones when the alternative is ``extra + null`` as in the
     tutorial, else the leading ones if names match).  The local simulations are cut into chunks of ``chunk``
-    (default: ``ceil(local / pipeline)`` clamped to 2048..8192) and up to ``pipeline`` chunks are in flight at once,
-    each on its own CUDA stream with its own simulator workspace: the few slowly converging fits that end every
-    batched L-BFGS (a latency-bound tail of ~1 ms rounds) then overlap the FFTs and the bulk of the other chunks'
-    fits instead of idling the GPU.
+    (default: one chunk of up to 16384 simulations; with the MCMC refinement and more than 8192 local simulations
+    ``ceil(local / pipeline)`` clamped to 2048..8192) and up to ``pipeline`` chunks are in flight at once, each on its own
+    CUDA stream with its own simulator workspace.
 
     ``simulator_kwargs``: passed to ``Simulator``; by default the regular grid is lengthened to the next 7-smooth length
     (``fft_length="fast"``: only binned lightcurves are used here, and the simulated process is statistically the same),
@@ -242,7 +241,15 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     opts = _native.MtgLbfgsOpts(int(max_iter), 10, 2.220446049250313e-09, 1e-5, 20, 0)
     pipeline = max(1, int(pipeline))
     if chunk is None:
-        chunk = min(8192, max(2048, -(-L // pipeline)))        # small shards: one chunk (every extra chunk adds a tail)
+        # One chunk for up to 16384 local simulations: since the fused TK95 kernels (csrc/mtg_tk95.cu) the three stages of a
+        # 10^4-simulation shard are 0.2 / 0.015 / 0.26 s of device work that each fill the device, and chunks in flight on
+        # several streams only add latency-bound tails and host-thread jitter (measured 0.45-0.60 s in one chunk against
+        # 0.48-0.90 s in three on two boxes; the reference grid, simulation-bound, is 2.0 s either way).  The MCMC refinement
+        # keeps the pipeline above two waves of ensembles: its short launches pack better from several streams.
+        if int(refine_walkers) > 0 and int(refine_steps) > 0 and L > 8192:
+            chunk = min(8192, max(2048, -(-L // pipeline)))
+        else:
+            chunk = min(max(L, 1), 16384)
     chunk = max(1, int(chunk))
     starts = list(range(0, L, chunk))
 
