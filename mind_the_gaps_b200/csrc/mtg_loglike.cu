@@ -36,6 +36,10 @@ constexpr int k1_min_blocks(int J) { return J <= K1_NARROW_J ? K1_NARROW_BLOCKS 
 #ifndef K1_UNROLL
 #define K1_UNROLL 2
 #endif
+#ifndef K1_WIDE_UNROLL
+#define K1_WIDE_UNROLL K1_UNROLL
+#endif
+constexpr int k1_unroll(int J) { return J <= K1_NARROW_J ? K1_UNROLL : K1_WIDE_UNROLL; }
 // (A hand-rotated software pipeline -- phi / u / v of step i + 1 computed beside the state update of step i through
 //  K1State::prepare / advance -- was measured and dropped: 1.36e8 vs 1.57e8 evaluations/s; the extra live registers
 //  cost more than the filled dependency bubbles gain at the 128-register cap.)
@@ -49,6 +53,7 @@ __global__ void __launch_bounds__(k1_threads(JR + 2 * JC), k1_min_blocks(JR + 2 
 k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
 {
     constexpr int K1_THREADS = k1_threads(JR + 2 * JC);
+    constexpr int UNR = k1_unroll(JR + 2 * JC);
     constexpr int NARR = SHARED ? 3 : 1;
     __shared__ alignas(128) double sm[2][NARR][K1_TILE];
     __shared__ alignas(8) uint64_t bar[2];
@@ -119,7 +124,7 @@ k1_loglike(const __grid_constant__ Plan pl, const BatchArgs a)
             __syncthreads();
         }
         const double *st_t = &sm[st][0][0];
-_Pragma(K1_STR(unroll K1_UNROLL))
+#pragma unroll UNR
         for (int i = 0; i < cnt; ++i) {
             const int n = n0 + i;
             const double tn = st_t[i];
