@@ -1,13 +1,12 @@
 #!/bin/bash
-# GPU box only: E13 (K6) after the 32-bit rank sort / lengthened window.  tag = $1
+# GPU box only: E13 (K6): tests, throughput per slot count (MTG_E13_SLOTS), cuFFT pair time per candidate window length, launch list.  tag = $1
 TAG=${1:-r03h}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_simulator_gpu.py tests/test_simulator_stats_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 tail -8 gpurun_out/${TAG}_pytest.log
-for SL in 2 3 4; do
-echo "--- fast grid, slots $SL"; MTG_E13_DEBUG=1 MTG_E13_SLOTS=$SL timeout 300 python tools/e13_probe.py 256 fast 2>&1 | tail -3
+for SL in 1 2 3 4; do
+echo "--- fast grid, slots $SL"; MTG_E13_SLOTS=$SL timeout 300 python tools/e13_probe.py 256 fast 2>&1 | tail -2
 done
-echo "--- fast grid, slots 3, radix only"; MTG_E13_COUNTING=0 MTG_E13_SLOTS=3 timeout 300 python tools/e13_probe.py 256 fast 2>&1 | tail -1
 echo "--- FFT lengths"; timeout 200 python tools/e13_fft_len_probe.py 2>&1 | tail -14
 echo "--- exact grid"; timeout 300 python tools/e13_probe.py 128 exact 2>&1 | tail -2
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/${TAG}_launches_e13.csv \
