@@ -375,8 +375,16 @@ struct E13Slot {
     int cap = 0;
     int lc = -1, it = 0, n = 0, cur = 0;               // state: lightcurve in flight, iteration, length, index of the current iterate
     double *dst = nullptr;
+    std::map<long long, cudaGraphExec_t> graphs;       // (n << 1 | cur) -> one captured iteration (tied to this slot's buffers)
+    bool graphs_ok = true;
+    void drop_graphs()
+    {
+        for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+    }
     void free_buffers()
     {
+        drop_graphs();
         cudaFree(x[0]); cudaFree(x[1]); cudaFree(A); cudaFree(sorted); cudaFree(part); cudaFree(std_); cudaFree(F);
         cudaFree(k32); cudaFree(k32o); cudaFree(perm); cudaFree(flag); cudaFree(tmp);
         x[0] = x[1] = A = sorted = part = std_ = nullptr; F = nullptr; k32 = k32o = nullptr; perm = flag = nullptr; tmp = nullptr; cap = 0;
@@ -395,6 +403,7 @@ struct E13Slot {
 };
 struct E13Large {
     std::vector<E13Slot> slots; int32_t *iota = nullptr; int iota_n = 0; cudaEvent_t ev_in = nullptr;
+    bool allow_graphs = false;                         // set by the caller: all series of the run have one length
     int32_t *h_iters = nullptr; int h_iters_n = 0;
     void release()
     {
@@ -513,8 +522,8 @@ static int e13_slot_begin(E13Slot &q, const double *src, int n, double mean, int
     return mtg_cuda_check(cudaGetLastError(), "E13 set-up");
 }
 
-// enqueue one iteration on slot q; its allclose flag lands in q.h_flag when q.ev completes
-static int e13_slot_iterate(E13Slot &q, const int32_t *iota)
+// the work of one iteration on slot q's stream; its allclose flag lands in q.h_flag
+static int e13_slot_enqueue(E13Slot &q, const int32_t *iota)
 {
     int rc;
     const int n = q.n, Mh = n / 2 + 1;
@@ -533,6 +542,52 @@ static int e13_slot_iterate(E13Slot &q, const int32_t *iota)
     cudaMemsetAsync(q.flag, 0, sizeof(int32_t), q.st);
     k_e13_match_check<<<g, 256, 0, q.st>>>(q.perm, q.sorted, x, adj, n, q.flag);
     cudaMemcpyAsync(q.h_flag, q.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, q.st);
+    return 0;
+}
+
+// MTG_E13_GRAPH=0: enqueue every iteration call by call instead of replaying its captured CUDA graph
+static bool e13_use_graphs()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MTG_E13_GRAPH"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+
+// enqueue one iteration on slot q; q.ev completes when its flag is in q.h_flag.  An iteration is ~21 launches (two cuFFT
+// transforms of four passes each, the radix sort's six kernels, five of our own) for ~150 us of device work, and one host
+// thread feeds every slot: the sequence is captured once per (length, buffer parity) and replayed as ONE graph launch, so a
+// slow host does not become the bottleneck (measured on a fast one: 288 -> 317 lightcurves/s with two slots, 351 -> 366 with
+// three).  Only for the lengthened grid, where every series has the same length: on the reference grid the two segment
+// lengths, two buffer parities and Bluestein plans make the captures themselves cost more than they save (120 -> 95 /s).
+static int e13_slot_iterate(E13Slot &q, const int32_t *iota, bool allow_graph)
+{
+    int rc;
+    if (allow_graph && e13_use_graphs() && q.graphs_ok) {
+        const long long key = ((long long)q.n << 1) | (long long)q.cur;
+        cudaGraphExec_t ge = nullptr;
+        auto it = q.graphs.find(key);
+        if (it != q.graphs.end()) ge = it->second;
+        else {
+            cufftHandle f, b;                     // plan creation allocates: not inside a capture
+            if ((rc = e13_slot_plan(q, q.n, true, &f)) || (rc = e13_slot_plan(q, q.n, false, &b))) return rc;
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(q.st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = e13_slot_enqueue(q, iota);
+                const cudaError_t e = cudaStreamEndCapture(q.st, &g);
+                if (!rc && e == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) q.graphs[key] = ge;
+                else { ge = nullptr; q.graphs_ok = false; }
+                if (g) cudaGraphDestroy(g);
+            } else q.graphs_ok = false;
+            cudaGetLastError();                   // a failed capture falls back to plain launches below
+        }
+        if (ge) {
+            MTG_CUDA(cudaGraphLaunch(ge, q.st));
+            cudaEventRecord(q.ev, q.st);
+            mtg_count_launch(20);
+            return mtg_cuda_check(cudaGetLastError(), "E13 iteration (graph)");
+        }
+    }
+    if ((rc = e13_slot_enqueue(q, iota))) return rc;
     cudaEventRecord(q.ev, q.st);
     mtg_count_launch(20);
     return mtg_cuda_check(cudaGetLastError(), "E13 iteration");
@@ -541,7 +596,7 @@ static int e13_slot_iterate(E13Slot &q, const int32_t *iota)
 static int e13_slots()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("MTG_E13_SLOTS"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > 8) v = 8; }
+    if (v < 0) { const char *e = getenv("MTG_E13_SLOTS"); v = e ? atoi(e) : 4; if (v < 1) v = 1; if (v > 8) v = 8; }
     return v;
 }
 
@@ -550,6 +605,7 @@ static int e13_large_prepare(E13Large &g, int n_max, int count)
     if ((int)g.slots.size() != e13_slots()) { g.release(); g.slots.resize(e13_slots()); }
     if (!g.ev_in) MTG_CUDA(cudaEventCreateWithFlags(&g.ev_in, cudaEventDisableTiming));
     if (g.iota_n < n_max) {
+        for (auto &q : g.slots) q.drop_graphs();             // the captured iterations point at the old index array
         cudaFree(g.iota); g.iota = nullptr; g.iota_n = 0;
         int rc = e13_alloc((void **)&g.iota, sizeof(int32_t) * (size_t)n_max);
         if (rc) return rc;
@@ -591,7 +647,7 @@ static int e13_run_large(E13Large &g, int count, const int *n, double *const *sr
             MTG_CUDA(cudaMemcpyAsync(q.x[1], src[k], sizeof(double) * n[k], cudaMemcpyDeviceToDevice, q.st));
             r = e13_slot_begin(q, nullptr, n[k], mean, pdf, nullptr, seed, lc_offset + k, true);
         } else r = e13_slot_begin(q, src[k], n[k], mean, pdf, variates ? variates[k] : nullptr, seed, lc_offset + k, false);
-        if (!r) r = e13_slot_iterate(q, g.iota);
+        if (!r) r = e13_slot_iterate(q, g.iota, g.allow_graphs);
         if (!r) ++active;
         return r;
     };
@@ -606,7 +662,7 @@ static int e13_run_large(E13Large &g, int count, const int *n, double *const *sr
             if (q.lc < 0) continue;
             if ((rc = mtg_cuda_check(cudaEventSynchronize(q.ev), "E13 iteration"))) break;
             const bool notclose = *q.h_flag != 0;
-            if (notclose && q.it < max_iter) { q.cur ^= 1; q.it += 1; rc = e13_slot_iterate(q, g.iota); continue; }
+            if (notclose && q.it < max_iter) { q.cur ^= 1; q.it += 1; rc = e13_slot_iterate(q, g.iota, g.allow_graphs); continue; }
             // converged (or out of iterations): the result is the CURRENT iterate, not the candidate (simulator.py:129)
             MTG_CUDA(cudaMemcpyAsync(q.dst, q.x[q.cur], sizeof(double) * q.n, cudaMemcpyDeviceToDevice, q.st));
             g.h_iters[q.lc] = q.it;
@@ -679,6 +735,7 @@ int sim_e13_chunk(Sim *s, int Lc, int l0, uint64_t seed, const double *d_pdf_var
         }
         if (all_long) {
             if (!s->e13_large) s->e13_large = new E13Large();
+            ((E13Large *)s->e13_large)->allow_graphs = n_pad != 0;
             return e13_run_large(*(E13Large *)s->e13_large, Lc, nn.data(), ptr.data(), ptr.data(), s->cfg.mean, s->cfg.pdf, max_iter,
                                  var ? vptr.data() : nullptr, seed, (uint64_t)l0, d_iters, stream);
         }

@@ -22,5 +22,6 @@ with warnings.catch_warnings():
         torch.cuda.synchronize(); t0 = time.perf_counter()
         rates, info = sim.generate_lightcurves(n_lc, seed=4 + rep, return_info=True)
         torch.cuda.synchronize(); wall = time.perf_counter() - t0
-        print("%d lcs: %.3f s  %.1f lc/s  iterations mean %.1f max %d  n_fft %d" % (n_lc, wall, n_lc / wall, np.mean(info["e13_iterations"]),
-              np.max(info["e13_iterations"]), sim.fftndatapoints), flush=True)
+        import hashlib
+        print("%d lcs: %.3f s  %.1f lc/s  iterations mean %.1f max %d  n_fft %d  sha1(rates) %s" % (n_lc, wall, n_lc / wall, np.mean(info["e13_iterations"]),
+              np.max(info["e13_iterations"]), sim.fftndatapoints, hashlib.sha1(np.ascontiguousarray(rates).tobytes()).hexdigest()[:12]), flush=True)
