@@ -290,10 +290,14 @@ static int host_eval(const mtg_model_t *model, int N, int S, int group, int B,
     }
     MTG_CUDA(cudaEventRecord(c.data_ready, c.stream));
     for (int i = 0; i < HostCtx::NPIPE; ++i) MTG_CUDA(cudaStreamWaitEvent(c.pipe[i], c.data_ready, 0));
+    // The first chunk is ONE wave: nothing overlaps its parameter upload, so the device starts after half the copy time
+    // (measured end to end on the C2 bench: see DESIGN.md section 1).
+    const size_t first = (S == 1) ? wave2 / 2 : (((wave2 / 2) + group - 1) / group) * (size_t)group;
     int k = 0;
-    for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk, ++k) {
-        const int Bc = (int)std::min(chunk, (size_t)B - b0);
+    for (size_t b0 = 0; b0 < (size_t)B; ++k) {
+        const int Bc = (int)std::min(k == 0 ? first : chunk, (size_t)B - b0);
         if ((rc = run_chunk(b0, Bc, c.pipe[k % HostCtx::NPIPE]))) break;
+        b0 += (size_t)Bc;
     }
     for (int i = 0; i < HostCtx::NPIPE; ++i) {
         cudaError_t e = cudaStreamSynchronize(c.pipe[i]);
