@@ -106,10 +106,10 @@ class ClockSampler(threading.Thread):
 
 
 def k1_profile_traffic():
-    """DRAM bytes per launch of the headline kernel from the committed ncu capture (profiles/r02c_k1_ncu_full_raw.csv:
+    """DRAM bytes per launch of the headline kernel from the committed ncu capture (profiles/r03t_k1_ncu_full_raw.csv:
     header row, unit row, value row); None when the file is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r02c_k1_ncu_full_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r03t_k1_ncu_full_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         head, units, vals = rows[0], rows[1], rows[2]
@@ -118,7 +118,7 @@ def k1_profile_traffic():
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = head.index(key)
             tot += float(vals[i].replace(",", "")) * scale[units[i]]
-        return tot, "profiles/r02c_k1_ncu_full_raw.csv"
+        return tot, "profiles/r03t_k1_ncu_full_raw.csv"
     except Exception:
         return None
 
