@@ -49,3 +49,24 @@ def test_struct_layout_matches_header():
     expect += 4 + 4 * n_par                                # n_free, free_idx
     expect = (expect + 7) // 8 * 8 + 16 * n_par            # lo, hi
     assert ctypes.sizeof(_native.MtgModel) == expect
+
+
+def test_sim_config_layout_and_flag_constants_match_header():
+    """mtg_sim_config_t: nine 4-byte / 8-byte scalars in the header's order, then six pointers; the MTG_SIM_* / enum
+    constants of the binding are the header's."""
+    text = open(os.path.join(ROOT, "include", "mtg_b200.h")).read()
+    body = re.search(r"typedef struct mtg_sim_config \{(.*?)\} mtg_sim_config_t;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [(t.strip(), n) for t, n in re.findall(r"([A-Za-z0-9_ ]+?[ \*])(\w+);", body)]
+    names = [n for _, n in fields]
+    assert names == [f[0] for f in _native.MtgSimConfig._fields_]
+    size = 0
+    for t, _ in fields:
+        w = 4 if t.startswith("int32_t") else 8
+        size = (size + w - 1) // w * w + w
+    assert ctypes.sizeof(_native.MtgSimConfig) == (size + 7) // 8 * 8
+    assert int(re.search(r"#define MTG_SIM_E13_PADDED (\d+)", text).group(1)) == _native.SIM_E13_PADDED
+    assert (_native.PDF_GAUSSIAN, _native.PDF_LOGNORMAL, _native.PDF_UNIFORM) == (0, 1, 2)
+    assert re.search(r"MTG_PDF_GAUSSIAN = 0, MTG_PDF_LOGNORMAL = 1, MTG_PDF_UNIFORM = 2", text)
+    assert re.search(r"MTG_NOISE_POISSON = 0, MTG_NOISE_KRAFT = 1, MTG_NOISE_GAUSSIAN = 2", text)
+    assert (_native.NOISE_POISSON, _native.NOISE_KRAFT, _native.NOISE_GAUSSIAN) == (0, 1, 2)
