@@ -360,9 +360,9 @@ static int e13_work_alloc(E13Work &w, int cnt, int n, int use_cnt = 0, int use_n
 // The batched loop above carries EVERY lightcurve of a batch through the FFT pair and the sort until the last one has
 // converged (max over the batch ~ 25 iterations where the mean is 19), and a batch of 1.3e6-point series streams every
 // array through HBM.  Long series therefore run one at a time: a slot (own stream, cuFFT plans and ~60 n bytes of work
-// arrays, which stay in the 126 MB L2 between the kernels of an iteration) carries ONE lightcurve to convergence, the
-// host reads its allclose flag after every iteration and hands the slot the next lightcurve as soon as it is done; two
-// slots keep the device busy while the host decides.  Accepting an iterate is a pointer swap, the rank matching and the
+// arrays) carries ONE lightcurve to convergence, the host reads its allclose flag after every iteration and hands the slot
+// the next lightcurve as soon as it is done; MTG_E13_SLOTS (default 4) slots keep the device busy while the host decides
+// (measured 188 / 288-317 / 351-366 / 383-390 lightcurves/s with 1 / 2 / 3 / 4).  Accepting an iterate is a pointer swap, the rank matching and the
 // allclose test are one kernel, and the series moments come from a grid-wide reduction instead of one CTA per series.
 #define E13_NB 296
 struct E13Slot {
