@@ -1,4 +1,5 @@
-"""K8 in the latency regime (hundreds to a few thousand ensembles of 30 walkers): MTG_K8_PIPE=0|1 A/B -- GPU box only."""
+"""K8 in the latency regime (hundreds to a few thousand ensembles of 30 walkers): ms per step against the ensemble count -- GPU box only.
+(Round 2 used it to A/B a software-pipelined variant of the likelihood loop, measured slower and removed: DESIGN.md section 4.)"""
 import ctypes, os, sys, hashlib
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
