@@ -173,6 +173,20 @@ def alternative_starts(x_alt0, x_null_best, null_slots, lo, hi, n_starts, rng):
     return np.clip(out, lo, hi)
 
 
+def default_chunk(n_local, pipeline=3, refine=False):
+    """Simulations per chunk of ``simulate_and_fit`` for a shard of ``n_local`` simulations.
+
+    One chunk for up to 16384 local simulations: since the fused TK95 kernels (csrc/mtg_tk95.cu) the three stages of a
+    10^4-simulation shard are 0.2 / 0.015 / 0.26 s of device work that each fill the device, and chunks in flight on several
+    streams only add latency-bound tails and host-thread jitter (measured 0.45-0.60 s in one chunk against 0.48-0.90 s in
+    three on two boxes; the reference grid, simulation-bound, is 2.0 s either way).  The MCMC refinement keeps the pipeline
+    above two waves of ensembles (8192 simulations): its short launches pack better from several streams."""
+    n_local = int(n_local)
+    if refine and n_local > 8192:
+        return min(8192, max(2048, -(-n_local // max(1, int(pipeline)))))
+    return min(max(n_local, 1), 16384)
+
+
 def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slots=None, pdf="Gaussian",
                      extension_factor=2, sigma_noise=None, n_starts_null=2, n_starts_alt=8, seed=0,
                      max_iter=200, device=None, distributed=None, chunk=None, pipeline=3, return_lightcurves=False,
@@ -241,15 +255,7 @@ def simulate_and_fit(lightcurve, null_kernel, alt_kernel, null_samples, null_slo
     opts = _native.MtgLbfgsOpts(int(max_iter), 10, 2.220446049250313e-09, 1e-5, 20, 0)
     pipeline = max(1, int(pipeline))
     if chunk is None:
-        # One chunk for up to 16384 local simulations: since the fused TK95 kernels (csrc/mtg_tk95.cu) the three stages of a
-        # 10^4-simulation shard are 0.2 / 0.015 / 0.26 s of device work that each fill the device, and chunks in flight on
-        # several streams only add latency-bound tails and host-thread jitter (measured 0.45-0.60 s in one chunk against
-        # 0.48-0.90 s in three on two boxes; the reference grid, simulation-bound, is 2.0 s either way).  The MCMC refinement
-        # keeps the pipeline above two waves of ensembles: its short launches pack better from several streams.
-        if int(refine_walkers) > 0 and int(refine_steps) > 0 and L > 8192:
-            chunk = min(8192, max(2048, -(-L // pipeline)))
-        else:
-            chunk = min(max(L, 1), 16384)
+        chunk = default_chunk(L, pipeline, int(refine_walkers) > 0 and int(refine_steps) > 0)
     chunk = max(1, int(chunk))
     starts = list(range(0, L, chunk))
 

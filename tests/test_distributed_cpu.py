@@ -22,6 +22,19 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_default_chunk_policy():
+    """One chunk per shard up to 16384 simulations; refined runs above two waves of ensembles keep the pipeline."""
+    for world in (1, 2, 4, 8):
+        a, b = lrt.shard_range(10000, 0, world)
+        assert lrt.default_chunk(b - a) == b - a                       # plain LRT: the whole shard in one chunk
+    assert lrt.default_chunk(0) == 1 and lrt.default_chunk(100000) == 16384
+    assert lrt.default_chunk(10000, pipeline=3, refine=True) == 3334   # refined, > 8192: ceil(n / pipeline) in 2048..8192
+    assert lrt.default_chunk(40000, pipeline=3, refine=True) == 8192
+    assert lrt.default_chunk(5000, pipeline=3, refine=True) == 5000    # refined, small shard: one chunk
+    chunks = lambda n, c: len(range(0, n, c))
+    assert chunks(10000, lrt.default_chunk(10000)) == 1 and chunks(10000, lrt.default_chunk(10000, 3, True)) == 3
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
